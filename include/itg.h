@@ -1,0 +1,177 @@
+/*
+ * itg.h -- C ABI of libitg_b200.so: B200 (sm_100a) kernels for the patch-by-patch Generator inference path
+ * of Infinite_Texture_GANs (local padding).
+ *
+ * The reference has no native code and no FFI: its "operator interface" for this path is the Python
+ * surface of models/layers.py, models/generators.py and utils.py.  Each entry point below names the
+ * reference code it replaces (file:line relative to the reference repo).  The Python mirror of that
+ * surface (infinite_texture_gans_b200/{layers,generators,utils}.py) binds these symbols with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns 0 on success and a negative code on error; itg_last_error() returns a
+ *     thread-local message.  No exceptions, no allocation, no implicit device synchronisation.
+ *   - the caller owns every buffer (device pointers unless stated otherwise) and passes the CUDA stream
+ *     (a cudaStream_t cast to void*).  Launches are stream-ordered and can be captured in a CUDA graph.
+ *   - one device per call: the current CUDA device of the calling thread.
+ *
+ * Data layout ("grid tensors")
+ *   The patch grid of the reference (B = nph*npw patches of r x r pixels, NCHW) is stored merged and
+ *   channels-last:  a tensor of H x W pixels (H = nph*r, W = npw*r) and C storage channels is a buffer
+ *   of (H+2) x (W+2) x C elements: the interior plus a 1-pixel FRAME.  The frame holds what LocalPadder
+ *   (models/layers.py:78-101) would concatenate around the merged image: the outer padding (replicate
+ *   or zeros), the stored halo row/column of the sequential protocol (models/layers.py:103-143), or a
+ *   neighbouring GPU's border row.  A conv therefore never materialises padded patches: tap (dy,dx) of
+ *   output pixel (y,x) reads buffer pixel (y+1+dy, x+1+dx).  `in`/`out` pointers below always address
+ *   the buffer origin (frame pixel (-1,-1)).  C is a multiple of 8; padded channels hold zeros.
+ */
+#ifndef ITG_H_
+#define ITG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITG_ABI_VERSION 1
+
+enum itg_status {
+  ITG_OK = 0,
+  ITG_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  ITG_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed */
+  ITG_ERR_UNSUPPORTED = -3   /* valid request this build cannot serve */
+};
+
+enum itg_dtype { ITG_F32 = 0, ITG_F16 = 1, ITG_BF16 = 2 };
+
+/* What the conv computes on its M-grid (the pixels it is evaluated on):
+ *   ITG_CONV3X3 : 9 taps dy,dx in {-1,0,1}; weight tap t = (dy+1)*3+(dx+1).     conv2d_lp, layers.py:29-36
+ *   ITG_CONV1X1 : 1 tap.                                                          conv1x1 shortcut, layers.py:294-299
+ *   ITG_UPCONV  : conv3x3(pad(nearest_up2(x))) evaluated as 4 output phases (a,b) of 2x2 taps on the
+ *                 low-res framed tensor with pre-summed weights; weight tap = phase*4 + i*2 + j,
+ *                 dy = a-1+i, dx = b-1+j, output pixel (2y+a, 2x+b).             generators.py:95-111 + layers.py:29-36
+ */
+enum itg_conv_mode { ITG_CONV3X3 = 0, ITG_CONV1X1 = 1, ITG_UPCONV = 2 };
+
+/* How the producer fills the frame of the tensors it writes (outer padding, layers.py:82-99):
+ * NONE leaves the frame untouched (the caller fills it: sequential halos, neighbour-GPU rows). */
+enum itg_border { ITG_BORDER_NONE = 0, ITG_BORDER_REPLICATE = 1, ITG_BORDER_CONSTANT = 2 };
+
+enum itg_residual { ITG_RES_NONE = 0, ITG_RES_GRID = 1 /* framed grid tensor, operand dtype */,
+                    ITG_RES_F32 = 2 /* unframed fp32 NHWC */ };
+
+enum itg_impl { ITG_IMPL_AUTO = 0 /* tcgen05 for 16-bit operands, direct for fp32 */,
+                ITG_IMPL_DIRECT = 1 /* CUDA-core direct conv (any dtype; the on-device cross-check) */,
+                ITG_IMPL_UMMA = 2 /* tcgen05 implicit GEMM (16-bit only) */ };
+
+enum itg_img_layout { ITG_IMG_MERGED = 0 /* (C, H, W) planar */, ITG_IMG_PATCHES = 1 /* (B, C, P, P) */ };
+
+/* One fused convolution launch.  Pointers are device pointers; unused ones are NULL.
+ *
+ * acc[y,x,n] = sum_taps sum_k W[tap][n][k] * in[y+dy, x+dx, in_c_off+k]            (fp32 accumulate)
+ * v          = acc + bias[n] (+ residual)
+ * SSM mode (mod_x != NULL, layers.py:228-234): columns are interleaved (gamma_c, beta_c) and
+ *   v_c = (1+gamma_c) * (x_c - mod_mean_c) * mod_rstd_c + beta_c,  x read from mod_x at (oy>>mod_shift, ox>>mod_shift)
+ * outputs (any subset):
+ *   out_raw : v                                   (grid tensor)
+ *   out_act : act(scale[n]*v + shift[n])          (grid tensor; BN eval + (Leaky)ReLU, frame per `border`)
+ *   out_f32 : v                                   (unframed fp32 NHWC, out_c channels)
+ *   out_img : tanh(v[0..img_c))                   (fp32 planar image, generators.py:119-121)
+ */
+typedef struct itg_conv_desc {
+  int32_t dtype;        /* itg_dtype of in / weights / grid outputs */
+  int32_t mode;         /* itg_conv_mode */
+  int32_t impl;         /* itg_impl */
+  int32_t border;       /* itg_border applied to out_act's frame */
+
+  const void* in;       /* framed grid tensor: pixel (-1,-1) of an (in_h+2) x (in_w+2) x in_c window */
+  int32_t in_h, in_w;   /* interior size of `in` == M-grid size */
+  int32_t in_pitch;     /* pixels between buffer rows of `in`; 0 = in_w + 2 (a window into a wider buffer otherwise) */
+  int32_t in_c;         /* storage channels of `in` (multiple of 8) */
+  int32_t in_c_off;     /* first channel of the slice this conv reads (multiple of 8) */
+  int32_t k;            /* channels contracted per tap (<= k_pad) */
+
+  const void* w;        /* [taps][n_pad][k_pad], operand dtype; taps = 9 | 1 | 16 */
+  int32_t n_pad;        /* GEMM N: multiple of 16, zero-padded rows */
+  int32_t k_pad;        /* multiple of 16 (64 when k > 64), zero-padded */
+  const float* bias;    /* [n_pad] or NULL */
+
+  int32_t out_h, out_w; /* interior size of the outputs (2*in_h, 2*in_w for ITG_UPCONV) */
+  int32_t out_c;        /* storage channels of out_raw / out_act / out_f32 (multiple of 8, <= n_pad; n_pad/2 in SSM mode) */
+
+  int32_t res_kind;     /* itg_residual */
+  int32_t res_shift;    /* residual read at (oy>>res_shift, ox>>res_shift) */
+  const void* res;
+  int32_t res_c;        /* storage channels of the residual tensor */
+  int32_t res_h, res_w; /* interior size of the residual tensor (ITG_RES_GRID) / its size (ITG_RES_F32) */
+
+  const void* mod_x;    /* SSM: grid tensor to modulate, operand dtype */
+  int32_t mod_c, mod_shift, mod_h, mod_w;
+  const float* mod_mean;  /* [out_c] running_mean   (layers.py:218) */
+  const float* mod_rstd;  /* [out_c] 1/sqrt(running_var+eps) */
+
+  void* out_raw;
+  void* out_act;
+  const float* scale;   /* [n_pad] BN eval scale  w/sqrt(var+eps); NULL = 1 */
+  const float* shift;   /* [n_pad] BN eval shift  b-mean*scale;    NULL = 0 */
+  float leak;           /* LeakyReLU slope (0 = ReLU) */
+  int32_t act_linear;   /* 1: out_act = scale*v+shift without activation (SSM shortcut bn3) */
+  float* out_f32;
+  float* out_img;
+  int32_t img_c;        /* image channels (generators.py:83) */
+  int32_t img_layout;   /* itg_img_layout */
+  int32_t patch;        /* P, for ITG_IMG_PATCHES */
+} itg_conv_desc;
+
+/* Library / ABI version (ITG_ABI_VERSION). */
+int itg_version(void);
+/* Message of the last failing call on this thread. */
+const char* itg_last_error(void);
+/* sizeof(itg_conv_desc) as compiled, so a binding can check its struct mirror. */
+int itg_conv_desc_size(void);
+
+/* conv2d_lp.forward + the elementwise ops around it (layers.py:29-36,301-322; generators.py:91-121). */
+int itg_conv_fwd(const itg_conv_desc* desc, void* stream);
+
+/* Attention.forward (layers.py:246-258) evaluated per patch of `patch` x `patch` pixels on a grid tensor
+ * of th x tw patches; C = channels (C/8 query/key, C/2 value channels).
+ * x: framed grid tensor (storage channels xc).  Weights are fp32: w_theta/w_phi [C/8][C], w_g [C/2][C],
+ * w_o [C][C/2], biases likewise; gamma is read from device memory (attention.gamma, layers.py:244).
+ * out_raw = gamma*o + x;  out_act = act(scale*out_raw + shift) with frame per `border`.  Either may be NULL. */
+int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int32_t patch, int32_t C, int32_t xc,
+                      const float* w_theta, const float* b_theta, const float* w_phi, const float* b_phi,
+                      const float* w_g, const float* b_g, const float* w_o, const float* b_o, const float* gamma,
+                      void* out_raw, void* out_act, const float* scale, const float* shift, float leak,
+                      int32_t border, void* stream);
+
+/* Host-supplied noise -> grid tensor.  src: fp32 planar (C, H, W) (the z grid with its random 1-px ring,
+ * utils.py:228, or an SSM map, utils.py:246); dst: (H x W x dst_c) channels-last in `dtype`, channels
+ * >= C zero-filled.  The whole H x W extent is copied: the caller interprets the outermost ring as the frame. */
+int itg_pack_nchw(int32_t dtype, const float* src, int32_t C, int32_t H, int32_t W, void* dst, int32_t dst_c,
+                  void* stream);
+
+/* SSM noise map (utils.py:246, one channel, fp32, Hm x Wm = interior + 4) -> stack of its nine 3x3 taps as a
+ * grid tensor with interior (Hm-2) x (Wm-2) and dst_c >= 16 channels (channel t = map shifted by tap t,
+ * channels >= 9 zero).  The first SSM conv `mlp_shared` (1 -> 128 channels, layers.py:220,229) is then an
+ * ITG_CONV1X1 launch with k = 16. */
+int itg_pack_map_taps(int32_t dtype, const float* src, int32_t Hm, int32_t Wm, void* dst, int32_t dst_c,
+                      void* stream);
+
+/* Copy a rectangle of pixels between grid tensors (all channels): the halo moves of the sequential
+ * protocol (layers.py:103-143) and of the row-band multi-GPU split.  Coordinates are buffer pixels
+ * (frame included); pitches are in pixels. */
+int itg_copy_rect(int32_t dtype, const void* src, int32_t src_pitch, int32_t sy, int32_t sx,
+                  void* dst, int32_t dst_pitch, int32_t dy, int32_t dx, int32_t h, int32_t w, int32_t c,
+                  void* stream);
+
+/* Fill the frame of a grid tensor from its interior (replicate) or with zeros (constant): F.pad of
+ * layers.py:82.  sides: bit0 top, bit1 bottom, bit2 left, bit3 right. */
+int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int32_t border, int32_t sides,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITG_H_ */

@@ -1,0 +1,253 @@
+// Implicit-GEMM local-padding convolution on the 5th-gen tensor cores (sm_100a): TMA -> shared memory ->
+// tcgen05.mma (accumulators in TMEM) -> tcgen05.ld -> fused epilogue.
+//
+// GEMM view:  D[m][n] = sum_{tap} sum_{k} A_tap[m][k] * W[tap][n][k]
+//   m : 128 M-grid pixels of a TH x TW tile (TH*TW = 128) of the merged grid tensor
+//   k : input channels (chunks of KC = 16/32/64 channels = one 32/64/128-byte swizzle row)
+//   n : output channels (GEMM columns), n_blk <= 256 per CTA
+// A_tap is the tile shifted by the tap offset (dy,dx): because the grid tensor carries its 1-pixel frame
+// (outer padding / sequential halo / neighbour-GPU halo), the shifted tile is one 3-D TMA box
+// {KC, TW, TH} at (c0, x0+dx+1, y0+dy+1) -- the local-padding "halo gather" is the TMA coordinate, and no
+// padded patch is ever materialised.  TMA zero-fills what lies beyond the buffer (partial tiles, channel tail).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4) .. +31).
+#pragma once
+#include <cuda.h>
+#include "itg_common.cuh"
+
+namespace itg {
+
+struct UmmaParams {
+  int m_h, m_w;          // M-grid size
+  int in_c_off;
+  int mode;
+  int tw_log2, tiles_x;
+  int n_pad, n_blk;
+  int kc, nchunks, ksteps_last;
+  int stages;
+  int a_bytes, b_bytes;  // per-stage operand bytes (also the TMA transaction size)
+  int a_stride, b_stride;  // 1024-aligned strides inside a stage
+  uint32_t sbo_enc;      // (8 * swizzle bytes) >> 4
+  uint32_t layout_type;  // UMMA smem-descriptor layout type: 2 = SW128, 4 = SW64, 6 = SW32
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  EpiParams ep;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a broken pipeline traps (the launch fails) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("itg: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kDummy = 0>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 / bf16 operands, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand descriptor: rows of `swizzle` bytes, 8-row groups SBO apart (canonical TMA swizzled layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_enc, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(sbo_enc & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int UMMA_THREADS = 256;
+constexpr int UMMA_BAR_BYTES = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_full = sbase;                 // [stages] x 8 B
+  const uint32_t bar_empty = sbase + 128;          // [stages] x 8 B
+  const uint32_t bar_acc = sbase + 256;            // accumulator complete
+  const uint32_t tmem_slot = sbase + 264;
+  const uint32_t stage0 = sbase + UMMA_BAR_BYTES;
+  const uint32_t stage_bytes = (uint32_t)(p.a_stride + p.b_stride);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * p.n_blk;
+  const int phase = blockIdx.z;
+  const int tw = 1 << p.tw_log2, th = 128 >> p.tw_log2;
+  const int y0 = (tile / p.tiles_x) * th, x0 = (tile % p.tiles_x) * tw;
+  const int ntaps = (p.mode == ITG_CONV3X3) ? 9 : (p.mode == ITG_CONV1X1 ? 1 : 4);
+
+  if (warp == 0) {
+    if (lane == 0) {                                                   // ---- TMA producer ----
+      int it = 0;
+      for (int t = 0; t < ntaps; ++t) {
+        int dy, dx, wt;
+        tap_offsets(p.mode, phase, t, dy, dx, wt);
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(p.a_bytes + p.b_bytes));
+          const uint32_t sa = stage0 + s * stage_bytes;
+          tma_load_3d(sa, &tm_a, bar_full + 8 * s, p.in_c_off + c * p.kc, x0 + dx + 1, y0 + dy + 1);
+          tma_load_2d(sa + p.a_stride, &tm_b, bar_full + 8 * s, c * p.kc, wt * p.n_pad + n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {                                                   // ---- MMA issuer ----
+      int it = 0;
+      for (int t = 0; t < ntaps; ++t) {
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = stage0 + s * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
+          const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
+          const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
+          for (int k = 0; k < nk; ++k)          // +32 B (16 channels) per K step inside the swizzle row
+            umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);       // frees the stage when these MMAs have read it
+        }
+      }
+      umma_commit(bar_acc);                      // accumulator complete
+    }
+    __syncwarp();
+  } else if (warp >= 4) {                                                // ---- epilogue ----
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const int y = y0 + (row >> p.tw_log2), x = x0 + (row & (tw - 1));
+    const bool valid = (y < p.m_h) && (x < p.m_w);
+    int oy = y, ox = x;
+    if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
+    for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      if (valid) {
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+        epilogue8<T>(p.ep, oy, ox, n0 + c0, a);
+        epilogue8<T>(p.ep, oy, ox, n0 + c0 + 8, b);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace itg

@@ -1,0 +1,321 @@
+// C ABI of libitg_b200.so (see include/itg.h).  Host-side validation, TMA tensor-map encoding and launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "attention.cuh"
+#include "conv_direct.cuh"
+#include "conv_umma.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define ITG_CUDA(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) return fail(ITG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+
+// tile width for an M-grid of width w: as wide as possible (coalesced rows) but no wider than the grid
+int pick_tw_log2(int w) {
+  int l = 5;                       // 32 x 4
+  while (l > 3 && (1 << l) > w) --l;   // down to 8 x 16
+  return l;
+}
+
+itg::EpiParams make_epi(const itg_conv_desc& d) {
+  itg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_h = d.out_h; ep.out_w = d.out_w; ep.out_c = d.out_c; ep.n_pad = d.n_pad;
+  ep.bias = d.bias;
+  ep.res_kind = d.res_kind; ep.res_shift = d.res_shift; ep.res_c = d.res_c; ep.res_h = d.res_h; ep.res_w = d.res_w;
+  ep.res = d.res;
+  ep.mod_x = d.mod_x; ep.mod_c = d.mod_c; ep.mod_shift = d.mod_shift; ep.mod_h = d.mod_h; ep.mod_w = d.mod_w;
+  ep.mod_mean = d.mod_mean; ep.mod_rstd = d.mod_rstd;
+  ep.out_raw = d.out_raw; ep.out_act = d.out_act; ep.scale = d.scale; ep.shift = d.shift; ep.leak = d.leak;
+  ep.act_linear = d.act_linear; ep.out_f32 = d.out_f32; ep.out_img = d.out_img; ep.img_c = d.img_c;
+  ep.img_layout = d.img_layout; ep.patch = d.patch; ep.border = d.border;
+  return ep;
+}
+
+int validate(const itg_conv_desc& d) {
+  if (d.dtype < ITG_F32 || d.dtype > ITG_BF16) return fail(ITG_ERR_INVALID, "conv: bad dtype %d", d.dtype);
+  if (d.mode < ITG_CONV3X3 || d.mode > ITG_UPCONV) return fail(ITG_ERR_INVALID, "conv: bad mode %d", d.mode);
+  if (!d.in || !d.w) return fail(ITG_ERR_INVALID, "conv: null input or weights");
+  if (d.in_h < 2 || d.in_w < 2) return fail(ITG_ERR_INVALID, "conv: grid %dx%d too small", d.in_h, d.in_w);
+  if (d.in_pitch != 0 && d.in_pitch < d.in_w + 2) return fail(ITG_ERR_INVALID, "conv: in_pitch %d < in_w + 2", d.in_pitch);
+  if (d.in_c % 8 || d.in_c_off % 8 || d.k % 8 || d.k <= 0 || d.in_c_off + d.k > d.in_c)
+    return fail(ITG_ERR_INVALID, "conv: channel slice off=%d k=%d of %d must be multiples of 8 and in range", d.in_c_off, d.k, d.in_c);
+  if (d.n_pad % 16 || d.n_pad <= 0) return fail(ITG_ERR_INVALID, "conv: n_pad %d must be a positive multiple of 16", d.n_pad);
+  if (d.k_pad % 16 || d.k_pad < d.k || (d.k_pad > 32 && d.k_pad % 64))
+    return fail(ITG_ERR_INVALID, "conv: k_pad %d must be 16, 32 or a multiple of 64 and >= k=%d", d.k_pad, d.k);
+  const int s = d.mode == ITG_UPCONV ? 2 : 1;
+  if (d.out_h != s * d.in_h || d.out_w != s * d.in_w)
+    return fail(ITG_ERR_INVALID, "conv: output %dx%d does not match grid %dx%d (scale %d)", d.out_h, d.out_w, d.in_h, d.in_w, s);
+  if (!d.out_img) {
+    if (d.out_c % 8 || d.out_c <= 0) return fail(ITG_ERR_INVALID, "conv: out_c %d must be a positive multiple of 8", d.out_c);
+    if (d.mod_x ? (2 * d.out_c > d.n_pad) : (d.out_c > d.n_pad))
+      return fail(ITG_ERR_INVALID, "conv: out_c %d exceeds the GEMM columns %d", d.out_c, d.n_pad);
+    if (!d.out_raw && !d.out_act && !d.out_f32) return fail(ITG_ERR_INVALID, "conv: no output");
+    if (d.mod_x && (!d.out_act || !d.mod_mean || !d.mod_rstd || d.out_raw || d.out_f32))
+      return fail(ITG_ERR_INVALID, "conv: SSM mode writes out_act only and needs mod_mean / mod_rstd");
+  } else if (d.img_c < 1 || d.img_c > 8) {
+    return fail(ITG_ERR_INVALID, "conv: img_c %d out of range", d.img_c);
+  } else if (d.img_layout == ITG_IMG_PATCHES && (d.patch <= 0 || d.out_h % d.patch || d.out_w % d.patch)) {
+    return fail(ITG_ERR_INVALID, "conv: patch %d does not tile the %dx%d image", d.patch, d.out_h, d.out_w);
+  }
+  if (d.res_kind != ITG_RES_NONE && (!d.res || d.res_c < d.out_c))
+    return fail(ITG_ERR_INVALID, "conv: residual tensor missing or too narrow");
+  return ITG_OK;
+}
+
+template <typename T>
+int launch_direct(const itg_conv_desc& d, cudaStream_t st) {
+  itg::DirectParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = d.in; p.in_h = d.in_h; p.in_w = d.in_w; p.in_pitch = d.in_pitch ? d.in_pitch : d.in_w + 2; p.in_c = d.in_c; p.in_c_off = d.in_c_off; p.k = d.k;
+  p.w = d.w; p.n_pad = d.n_pad; p.k_pad = d.k_pad; p.mode = d.mode;
+  p.tw_log2 = pick_tw_log2(d.in_w);
+  const int tw = 1 << p.tw_log2, th = 128 >> p.tw_log2;
+  p.tiles_x = (d.in_w + tw - 1) / tw;
+  const int tiles_y = (d.in_h + th - 1) / th;
+  p.ep = make_epi(d);
+  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(d.n_pad / itg::DIRECT_NB), d.mode == ITG_UPCONV ? 4u : 1u);
+  itg::conv_direct_kernel<T><<<grid, 128, 0, st>>>(p);
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+template <typename T>
+int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return fail(ITG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+
+  itg::UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_h = d.in_h; p.m_w = d.in_w; p.in_c_off = d.in_c_off; p.mode = d.mode;
+  p.tw_log2 = pick_tw_log2(d.in_w);
+  const int tw = 1 << p.tw_log2, th = 128 >> p.tw_log2;
+  p.tiles_x = (d.in_w + tw - 1) / tw;
+  const int tiles_y = (d.in_h + th - 1) / th;
+  p.n_pad = d.n_pad;
+  const int nblocks = (d.n_pad + 255) / 256;
+  if (d.n_pad % (16 * nblocks)) return fail(ITG_ERR_INVALID, "conv: n_pad %d must be a multiple of %d", d.n_pad, 16 * nblocks);
+  p.n_blk = d.n_pad / nblocks;
+  p.kc = d.k_pad >= 64 ? 64 : d.k_pad;
+  p.nchunks = d.k_pad / p.kc;
+  // the last chunk only issues the K steps that cover real channels
+  int kc_used = (d.k + p.kc - 1) / p.kc;                  // chunks that contain real channels
+  if (kc_used < 1) kc_used = 1;
+  p.nchunks = kc_used;
+  p.ksteps_last = (d.k - (kc_used - 1) * p.kc + 15) / 16;
+  const int swz = p.kc * 2;                                // bytes per swizzle row
+  p.sbo_enc = (uint32_t)(8 * swz) >> 4;
+  p.layout_type = swz == 128 ? 2u : (swz == 64 ? 4u : 6u);
+  p.a_bytes = 128 * swz;
+  p.b_bytes = p.n_blk * swz;
+  p.a_stride = (p.a_bytes + 1023) & ~1023;
+  p.b_stride = (p.b_bytes + 1023) & ~1023;
+  const int ntaps = d.mode == ITG_CONV3X3 ? 9 : (d.mode == ITG_CONV1X1 ? 1 : 4);
+  const int total_iters = ntaps * p.nchunks;
+  const int stage_bytes = p.a_stride + p.b_stride;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages > total_iters) stages = total_iters;
+  if (stages < 1) return fail(ITG_ERR_UNSUPPORTED, "conv: stage of %d bytes does not fit shared memory", stage_bytes);
+  p.stages = stages;
+  uint32_t cols = 32;
+  while ((int)cols < p.n_blk) cols <<= 1;
+  p.tmem_cols = cols;
+  const uint32_t fmt = (d.dtype == ITG_BF16) ? 1u : 0u;    // kind::f16 operand format
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_blk >> 3) << 17) | ((128u >> 4) << 24);
+  p.ep = make_epi(d);
+
+  const CUtensorMapDataType dt = (d.dtype == ITG_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tm_a, tm_b;
+  {
+    // activations: (C, W+2, H+2), channels innermost
+    cuuint64_t dims[3] = {(cuuint64_t)d.in_c, (cuuint64_t)(d.in_w + 2), (cuuint64_t)(d.in_h + 2)};
+    const int pitch = d.in_pitch ? d.in_pitch : d.in_w + 2;
+    cuuint64_t strides[2] = {(cuuint64_t)d.in_c * 2, (cuuint64_t)d.in_c * 2 * (cuuint64_t)pitch};
+    cuuint32_t box[3] = {(cuuint32_t)p.kc, (cuuint32_t)tw, (cuuint32_t)th};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&tm_a, dt, 3, const_cast<void*>(d.in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ITG_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed with %d", (int)r);
+  }
+  {
+    // weights: (k_pad, taps*n_pad)
+    const int taps_w = d.mode == ITG_CONV3X3 ? 9 : (d.mode == ITG_CONV1X1 ? 1 : 16);
+    cuuint64_t dims[2] = {(cuuint64_t)d.k_pad, (cuuint64_t)taps_w * (cuuint64_t)d.n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)d.k_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)p.n_blk};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tm_b, dt, 2, const_cast<void*>(d.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ITG_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  }
+
+  const int smem = itg::UMMA_BAR_BYTES + stages * stage_bytes + 1024;
+  static int smem_set_h = 0, smem_set_b = 0;
+  int& smem_set = (d.dtype == ITG_BF16) ? smem_set_b : smem_set_h;
+  if (smem > smem_set) {
+    ITG_CUDA(cudaFuncSetAttribute(itg::conv_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)nblocks, d.mode == ITG_UPCONV ? 4u : 1u);
+  itg::conv_umma_kernel<T><<<grid, itg::UMMA_THREADS, smem, st>>>(tm_a, tm_b, p);
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int blocks_for(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  if (b > 148 * 32) b = 148 * 32;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int itg_version(void) { return ITG_ABI_VERSION; }
+const char* itg_last_error(void) { return g_err; }
+int itg_conv_desc_size(void) { return (int)sizeof(itg_conv_desc); }
+
+int itg_conv_fwd(const itg_conv_desc* desc, void* stream) {
+  if (!desc) return fail(ITG_ERR_INVALID, "conv: null descriptor");
+  const itg_conv_desc& d = *desc;
+  int rc = validate(d);
+  if (rc != ITG_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int impl = d.impl;
+  if (impl == ITG_IMPL_AUTO) impl = (d.dtype == ITG_F32) ? ITG_IMPL_DIRECT : ITG_IMPL_UMMA;
+  if (impl == ITG_IMPL_UMMA) {
+    if (d.dtype == ITG_F16) return launch_umma<__half>(d, st);
+    if (d.dtype == ITG_BF16) return launch_umma<__nv_bfloat16>(d, st);
+    return fail(ITG_ERR_UNSUPPORTED, "conv: the tcgen05 path needs 16-bit operands");
+  }
+  if (d.dtype == ITG_F32) return launch_direct<float>(d, st);
+  if (d.dtype == ITG_F16) return launch_direct<__half>(d, st);
+  return launch_direct<__nv_bfloat16>(d, st);
+}
+
+int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int32_t patch, int32_t C, int32_t xc,
+                      const float* w_theta, const float* b_theta, const float* w_phi, const float* b_phi,
+                      const float* w_g, const float* b_g, const float* w_o, const float* b_o, const float* gamma,
+                      void* out_raw, void* out_act, const float* scale, const float* shift, float leak,
+                      int32_t border, void* stream) {
+  if (!x || !w_theta || !w_phi || !w_g || !w_o || !b_theta || !b_phi || !b_g || !b_o || !gamma)
+    return fail(ITG_ERR_INVALID, "attention: null argument");
+  if (C % 8 || C / 8 > itg::ATT_C8 || C / 2 > itg::ATT_C2 || xc % 8 || xc < C)
+    return fail(ITG_ERR_INVALID, "attention: C=%d (storage %d) unsupported (C %% 8 == 0, C <= %d)", C, xc, 2 * itg::ATT_C2);
+  if (patch != 16 && patch != 8) return fail(ITG_ERR_UNSUPPORTED, "attention: patch %d (supported: 8, 16)", patch);
+  if (!out_raw && !out_act) return fail(ITG_ERR_INVALID, "attention: no output");
+  itg::AttnParams p;
+  p.x = x; p.th = th; p.tw = tw; p.patch = patch; p.C = C; p.xc = xc;
+  p.w_theta = w_theta; p.b_theta = b_theta; p.w_phi = w_phi; p.b_phi = b_phi; p.w_g = w_g; p.b_g = b_g;
+  p.w_o = w_o; p.b_o = b_o; p.gamma = gamma; p.out_raw = out_raw; p.out_act = out_act; p.scale = scale; p.shift = shift;
+  p.leak = leak; p.border = border;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int npool = (patch / 2) * (patch / 2), npx = patch * patch;
+  const int smem = (int)sizeof(float) * (npx * (itg::ATT_C8 + itg::ATT_C2) + npool * (itg::ATT_C8 + itg::ATT_C2));
+  const dim3 grid((unsigned)(th * tw));
+#define ITG_ATT(T, NP)                                                                                         \
+  do {                                                                                                         \
+    ITG_CUDA(cudaFuncSetAttribute(itg::attention_kernel<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    itg::attention_kernel<T, NP><<<grid, NP * 4, smem, st>>>(p);                                                  \
+  } while (0)
+  if (patch == 16) {
+    if (dtype == ITG_F32) ITG_ATT(float, 64); else if (dtype == ITG_F16) ITG_ATT(__half, 64); else ITG_ATT(__nv_bfloat16, 64);
+  } else {
+    if (dtype == ITG_F32) ITG_ATT(float, 16); else if (dtype == ITG_F16) ITG_ATT(__half, 16); else ITG_ATT(__nv_bfloat16, 16);
+  }
+#undef ITG_ATT
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int itg_pack_nchw(int32_t dtype, const float* src, int32_t C, int32_t H, int32_t W, void* dst, int32_t dst_c, void* stream) {
+  if (!src || !dst || dst_c % 8 || dst_c < C || C < 1 || H < 1 || W < 1) return fail(ITG_ERR_INVALID, "pack: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)H * W * (dst_c / 8);
+  const int blocks = blocks_for(total, 256);
+  if (dtype == ITG_F32) itg::pack_nchw_kernel<float><<<blocks, 256, 0, st>>>(src, C, H, W, (float*)dst, dst_c);
+  else if (dtype == ITG_F16) itg::pack_nchw_kernel<__half><<<blocks, 256, 0, st>>>(src, C, H, W, (__half*)dst, dst_c);
+  else if (dtype == ITG_BF16) itg::pack_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, C, H, W, (__nv_bfloat16*)dst, dst_c);
+  else return fail(ITG_ERR_INVALID, "pack: bad dtype");
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int itg_pack_map_taps(int32_t dtype, const float* src, int32_t Hm, int32_t Wm, void* dst, int32_t dst_c, void* stream) {
+  if (!src || !dst || dst_c % 8 || dst_c < 16 || Hm < 3 || Wm < 3) return fail(ITG_ERR_INVALID, "pack_map_taps: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = blocks_for((size_t)(Hm - 2) * (Wm - 2) * (dst_c / 8), 256);
+  if (dtype == ITG_F32) itg::pack_map_taps_kernel<float><<<blocks, 256, 0, st>>>(src, Hm, Wm, (float*)dst, dst_c);
+  else if (dtype == ITG_F16) itg::pack_map_taps_kernel<__half><<<blocks, 256, 0, st>>>(src, Hm, Wm, (__half*)dst, dst_c);
+  else if (dtype == ITG_BF16) itg::pack_map_taps_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, Hm, Wm, (__nv_bfloat16*)dst, dst_c);
+  else return fail(ITG_ERR_INVALID, "pack_map_taps: bad dtype");
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int itg_copy_rect(int32_t dtype, const void* src, int32_t src_pitch, int32_t sy, int32_t sx, void* dst, int32_t dst_pitch,
+                  int32_t dy, int32_t dx, int32_t h, int32_t w, int32_t c, void* stream) {
+  if (!src || !dst || c % 8 || h < 0 || w < 0) return fail(ITG_ERR_INVALID, "copy_rect: bad arguments");
+  if (h == 0 || w == 0) return ITG_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = blocks_for((size_t)h * w * (c / 8), 256);
+  if (dtype == ITG_F32) itg::copy_rect_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, src_pitch, sy, sx, (float*)dst, dst_pitch, dy, dx, h, w, c);
+  else if (dtype == ITG_F16) itg::copy_rect_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)src, src_pitch, sy, sx, (__half*)dst, dst_pitch, dy, dx, h, w, c);
+  else if (dtype == ITG_BF16) itg::copy_rect_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, src_pitch, sy, sx, (__nv_bfloat16*)dst, dst_pitch, dy, dx, h, w, c);
+  else return fail(ITG_ERR_INVALID, "copy_rect: bad dtype");
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int32_t border, int32_t sides, void* stream) {
+  if (!t || c % 8 || h < 1 || w < 1 || (border != ITG_BORDER_REPLICATE && border != ITG_BORDER_CONSTANT))
+    return fail(ITG_ERR_INVALID, "fill_frame: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = blocks_for((size_t)(2 * (w + 2) + 2 * h) * (c / 8), 256);
+  if (dtype == ITG_F32) itg::fill_frame_kernel<float><<<blocks, 256, 0, st>>>((float*)t, h, w, c, border, sides);
+  else if (dtype == ITG_F16) itg::fill_frame_kernel<__half><<<blocks, 256, 0, st>>>((__half*)t, h, w, c, border, sides);
+  else if (dtype == ITG_BF16) itg::fill_frame_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)t, h, w, c, border, sides);
+  else return fail(ITG_ERR_INVALID, "fill_frame: bad dtype");
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""Host-side sampler: mirror of the reference's utils.py surface for the patch-by-patch inference path.
+
+`sample_from_gen_PatchByPatch_test` keeps the reference signature (utils.py:258-259) and noise draw
+order (utils.py:228, 246: one `torch.randn` for the whole z grid, then one per SSM level), so the same
+torch seed gives the same texture.  Two schedules:
+
+* ``schedule='oneshot'`` (default): the whole total_h x total_w patch grid is one device-resident forward
+  (what the training-time sampler utils.py:475-527 does with `LocalPadder.set_attributes(total_h, total_w)`;
+  bit-for-bit what the sequential schedule produces unless attention.gamma != 0).  No patch
+  is computed twice, nothing crosses the PCIe bus between layers.
+* ``schedule='sequential'``: the shipped schedule -- num_patches_height x num_patches_width sub-images with
+  stored halos (models/layers.py:103-143) and drop/regenerate of the last patch row / column
+  (utils.py:364-377) -- for exact reproduction of trained checkpoints with attention.
+"""
+from __future__ import annotations
+
+from math import ceil
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .layers import LocalPadder
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry and patch <-> image plumbing (utils.py:294-303, 577-613, 658-742)
+# ------------------------------------------------------------------------------------------------
+def patch_grid_geometry(output_resolution_height: int, output_resolution_width: int, n_layers_G: int, base_res: int = 4,
+                        num_patches_height: int = 3, num_patches_width: int = 3) -> Dict[str, int]:
+    """steps / total patch counts of utils.py:294-303."""
+    P = (2 ** (n_layers_G - 1)) * base_res
+    if num_patches_height < 2 or num_patches_width < 2:
+        raise ValueError("the sub-image needs at least 2 x 2 patches (one is dropped and regenerated per step)")
+    steps_h = ceil((output_resolution_height / P - 1) / (num_patches_height - 1))
+    steps_w = ceil((output_resolution_width / P - 1) / (num_patches_width - 1))
+    if steps_h < 1 or steps_w < 1:
+        raise ValueError(f"output {output_resolution_height}x{output_resolution_width} must exceed one patch ({P} px) per "
+                         "side (utils.py:317-395 fails with an UnboundLocalError there)")
+    return dict(P=P, steps_h=steps_h, steps_w=steps_w, total_h=steps_h * (num_patches_height - 1) + 1,
+                total_w=steps_w * (num_patches_width - 1) + 1)
+
+
+def image_location_of(ind_h: int, ind_w: int, steps_h: int, steps_w: int) -> str:
+    """Location strings of utils.py:321-337."""
+    row = "1st_row_last_row" if steps_h == 1 else ("1st_row" if ind_h == 0 else ("last_row" if ind_h == steps_h - 1 else "inter_row"))
+    col = "_1st_col_last_col" if steps_w == 1 else ("_1st_col" if ind_w == 0 else ("_last_col" if ind_w == steps_w - 1 else "_inter_col"))
+    return row + col
+
+
+def crop_images(images: torch.Tensor, crop_height: int, crop_width: int, stride: int, device=None) -> torch.Tensor:
+    """Sliding-window crops, row-major, images outermost (utils.py:658-742): (N,C,H,W) -> (N*P,C,ch,cw) fp32."""
+    N, C, H, W = images.shape
+    win = images.unfold(2, crop_height, stride).unfold(3, crop_width, stride)     # (N,C,ny,nx,ch,cw)
+    out = win.permute(0, 2, 3, 1, 4, 5).reshape(-1, C, crop_height, crop_width).float()
+    return out if device is None else out.to(device)
+
+
+def merge_patches_into_image(patches: torch.Tensor, num_patches_height: int, num_patches_width: int, device=None) -> torch.Tensor:
+    """Inverse of a non-overlapping crop (utils.py:577-613): (B,C,h,w) -> (B/(nph*npw), C, nph*h, npw*w) fp32."""
+    B, C, h, w = patches.shape
+    n = B // (num_patches_height * num_patches_width)
+    x = patches.reshape(n, num_patches_height, num_patches_width, C, h, w).permute(0, 3, 1, 4, 2, 5)
+    out = x.reshape(n, C, num_patches_height * h, num_patches_width * w).float()
+    return out if device is None else out.to(device)
+
+
+def draw_noise(num_images: int, z_dim: int, base_res: int, n_layers_G: int, map_dim: int, type_norm: str, total_h: int,
+               total_w: int) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
+    """Full-grid noise in the reference's draw order on the host RNG (utils.py:228 then :246 per level)."""
+    z = torch.randn(num_images, z_dim, total_h * base_res + 2, total_w * base_res + 2)
+    maps = None
+    if type_norm == "SSM":
+        maps = [torch.randn(num_images, map_dim, total_h * base_res * 2 ** i + 4, total_w * base_res * 2 ** i + 4)
+                for i in range(n_layers_G)]
+    return z, maps
+
+
+def build_z(num_images=1, z_dim=128, base_res=4, num_patches_height=3, num_patches_width=3, total_num_patches_height=3,
+            total_num_patches_width=3, device="cpu"):
+    """utils.py:221-234: overlapping sub-image crops of the full latent grid (with its random 1-px ring)."""
+    z, _ = draw_noise(num_images, z_dim, base_res, 0, 1, "BN", total_num_patches_height, total_num_patches_width)
+    return crop_images(z.to(device), num_patches_height * base_res + 2, num_patches_width * base_res + 2,
+                       (num_patches_width - 1) * base_res)
+
+
+def build_maps(num_images=1, map_dim=1, n_layers_G=4, base_res=4, num_patches_height=3, num_patches_width=3,
+               total_num_patches_height=3, total_num_patches_width=3, device="cpu"):
+    """utils.py:237-256: per level, overlapping sub-image crops of the full noise map (4-px over-size)."""
+    out = []
+    for i in range(n_layers_G):
+        r = base_res * 2 ** i
+        m = torch.randn(num_images, map_dim, total_num_patches_height * r + 4, total_num_patches_width * r + 4).to(device)
+        out.append(crop_images(m, num_patches_height * r + 4, num_patches_width * r + 4, (num_patches_width - 1) * r))
+    return out
+
+
+def _unwrap(netG):
+    return netG.module if isinstance(netG, nn.DataParallel) else netG
+
+
+# ------------------------------------------------------------------------------------------------
+# samplers
+# ------------------------------------------------------------------------------------------------
+def generate_full_grid(netG, z_full: torch.Tensor, maps_full: Optional[Sequence[torch.Tensor]] = None, graph: bool = False) -> torch.Tensor:
+    """One-shot forward of a whole patch grid.  z_full: (1, z_dim, th*b+2, tw*b+2) host or device fp32;
+    maps_full: per level (1, 1, th*r+4, tw*r+4).  Returns the device-resident (1, img_ch, th*P, tw*P) image
+    (the engine's output buffer: valid until the next call on the same grid size)."""
+    G = _unwrap(netG)
+    b = G.cfg.base_res
+    th, tw = (z_full.shape[-2] - 2) // b, (z_full.shape[-1] - 2) // b
+    if z_full.shape[0] != 1:
+        raise ValueError("one texture per call (utils.py:341 ignores num_images as well)")
+    eng = G.engine()
+    return eng.forward(z_full[0], None if maps_full is None else [m[0, 0] for m in maps_full], th=th, tw=tw,
+                       img_layout=L.IMG_MERGED, graph=graph)
+
+
+def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, num_images=1, num_patches_height=3,
+                                      num_patches_width=3, device="cpu", output_resolution_height=384,
+                                      output_resolution_width=384, schedule: str = "oneshot", noise=None,
+                                      return_on_device: bool = False, graph: bool = False) -> torch.Tensor:
+    """Generate one (1, img_ch, H, W) texture (utils.py:258-397).  Returns a host fp32 tensor like the
+    reference (each of its sub-images is `.cpu()`-ed, utils.py:360) unless return_on_device.
+
+    noise: optional (z_full, maps_full) to use instead of drawing from the global host RNG.
+    graph: replay the one-shot launch list from a CUDA graph (captured on first use per grid size)."""
+    G = _unwrap(netG)
+    n_layers_G, type_norm = G.n_layers_G, G.type_norm
+    geo = patch_grid_geometry(output_resolution_height, output_resolution_width, n_layers_G, base_res,
+                              num_patches_height, num_patches_width)
+    P, th, tw = geo["P"], geo["total_h"], geo["total_w"]
+    if noise is None:
+        z_full, maps_full = draw_noise(num_images, z_dim, base_res, n_layers_G, map_dim, type_norm, th, tw)
+    else:
+        z_full, maps_full = noise
+    z_full = z_full[:1]                      # utils.py:341 only ever uses the first image's crops
+    if maps_full is not None:
+        maps_full = [m[:1] for m in maps_full]
+    H, W = output_resolution_height, output_resolution_width
+    if schedule == "oneshot":
+        img = generate_full_grid(netG, z_full, maps_full, graph=graph)[:, :, :H, :W]
+        return img if return_on_device else img.cpu()
+    if schedule != "sequential":
+        raise ValueError("schedule must be 'oneshot' or 'sequential'")
+
+    # ---- the shipped schedule (utils.py:317-392) with on-device halos and on-device assembly ----
+    dev = next(G.parameters()).device
+    nph, npw, b = num_patches_height, num_patches_width, base_res
+    saved = (LocalPadder.num_patches_h, LocalPadder.num_patches_w)
+    LocalPadder.num_patches_h, LocalPadder.num_patches_w = nph, npw
+    try:
+        canvas = torch.empty((1, G.img_ch, th * P, tw * P), dtype=torch.float32, device=dev)
+        z_dev = z_full.to(dev)
+        maps_dev = None if maps_full is None else [m.to(dev) for m in maps_full]
+        sh, sw = geo["steps_h"], geo["steps_w"]
+        for ih in range(sh):
+            for iw in range(sw):
+                loc = image_location_of(ih, iw, sh, sw)
+                py, px = ih * (nph - 1), iw * (npw - 1)                   # top-left patch of this sub-image
+                z_sub = z_dev[:, :, py * b:(py + nph) * b + 2, px * b:(px + npw) * b + 2]
+                maps = None
+                if maps_dev is not None:
+                    maps = [m[:, :, py * b * 2 ** i:(py + nph) * b * 2 ** i + 4, px * b * 2 ** i:(px + npw) * b * 2 ** i + 4]
+                            for i, m in enumerate(maps_dev)]
+                patches = G(z_sub.contiguous(), maps, loc)
+                sub = merge_patches_into_image(patches, nph, npw)
+                kh = nph * P if ih == sh - 1 else (nph - 1) * P          # utils.py:364-377
+                kw = npw * P if iw == sw - 1 else (npw - 1) * P
+                canvas[:, :, py * P:py * P + kh, px * P:px * P + kw] = sub[:, :, :kh, :kw]
+    finally:
+        LocalPadder.num_patches_h, LocalPadder.num_patches_w = saved
+    img = canvas[:, :, :H, :W]
+    return img if return_on_device else img.cpu()

@@ -1,0 +1,253 @@
+"""Launch-by-launch parity of the CUDA kernels (through the C ABI) with the CPU emulation of the same
+descriptors (tests/emulator.py), on identical operands.
+
+Tolerances: fp32 direct conv <= 2e-5 relative to the output scale (fp32 re-association only); 16-bit paths
+are fed the *same* 16-bit-rounded operands as the emulator, so what remains is fp32 accumulation order plus
+one rounding of the stored result: <= 2^-9 (fp16) / 2^-6 (bf16) of the output scale.
+"""
+import math
+
+import pytest
+import torch
+
+from emulator import EmulatorBackend
+from infinite_texture_gans_b200 import _lib as L
+from infinite_texture_gans_b200 import packing as PK
+from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid, c_store
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+REL = {torch.float32: 2e-5, torch.float16: 2.0 ** -9, torch.bfloat16: 2.0 ** -6}
+
+
+@pytest.fixture(scope="module")
+def be():
+    from infinite_texture_gans_b200.ops import CudaBackend
+    return CudaBackend()
+
+
+def _grid(h, w, c, dtype, gen, device="cpu", scale=1.0):
+    buf = (torch.randn((h + 2, w + 2, c), generator=gen) * scale).to(dtype)
+    return Grid(buf.to(device), h, w, c)
+
+
+def _clone_grid(g: Grid, device):
+    return Grid(g.buf.clone().to(device), g.h, g.w, g.c)
+
+
+def _empty_like(g: Grid, device, fill=7.0):
+    return Grid(torch.full_like(g.buf, fill).to(device), g.h, g.w, g.c)
+
+
+def _cmp(name, got: torch.Tensor, ref: torch.Tensor, dtype):
+    got, ref = got.float().cpu(), ref.float()
+    scale = max(ref.abs().max().item(), 1e-6)
+    err = (got - ref).abs().max().item()
+    assert err <= REL[dtype] * scale + 1e-6, f"{name}: max-abs {err:.3e} at output scale {scale:.3e}"
+
+
+def _run_both(be, op_cpu: ConvOp, to_dev):
+    """Run op on the emulator (CPU tensors) and its device copy through the C ABI."""
+    EmulatorBackend().conv(op_cpu)
+    op_gpu = to_dev(op_cpu)
+    be.conv(op_gpu)
+    torch.cuda.synchronize()
+    return op_gpu
+
+
+CONV_CASES = [
+    # (mode, H, W, cin, cout, extras)
+    ("3x3", 12, 20, 128, 416, dict(raw=True, act=True, border=L.BORDER_REPLICATE)),
+    ("3x3", 12, 20, 416, 416, dict(act=True, border=L.BORDER_CONSTANT)),
+    ("3x3", 17, 33, 64, 64, dict(raw=True, act=True, res=0, border=L.BORDER_REPLICATE)),
+    ("3x3", 16, 24, 104, 104, dict(raw=True, res=1, border=L.BORDER_NONE)),
+    ("3x3", 33, 70, 52, 52, dict(act=True, res=1, border=L.BORDER_REPLICATE)),
+    ("3x3", 40, 48, 26, 26, dict(raw=True, act=True, border=L.BORDER_REPLICATE)),
+    ("3x3", 64, 40, 13, 13, dict(act=True, border=L.BORDER_REPLICATE)),
+    ("3x3", 9, 5, 8, 8, dict(raw=True, act=True, border=L.BORDER_REPLICATE)),
+    ("3x3", 48, 80, 13, 3, dict(img=L.IMG_MERGED)),
+    ("3x3", 32, 64, 16, 3, dict(img=L.IMG_PATCHES, patch=16)),
+    ("1x1", 12, 20, 416, 208, dict(raw=True)),
+    ("1x1", 19, 21, 26, 13, dict(raw=True)),
+    ("1x1", 30, 14, 16, 128, dict(act=True, relu=True)),
+    ("up", 12, 20, 416, 208, dict(act=True, border=L.BORDER_REPLICATE)),
+    ("up", 9, 13, 104, 52, dict(act=True, border=L.BORDER_CONSTANT)),
+    ("up", 24, 40, 26, 13, dict(act=True, border=L.BORDER_REPLICATE)),
+    ("up", 7, 6, 8, 8, dict(act=True, raw=True, border=L.BORDER_REPLICATE)),
+]
+
+
+def _make_conv(mode, H, W, cin, cout, ex, dtype, impl, seed):
+    g = torch.Generator().manual_seed(seed)
+    kin, kout = c_store(cin), c_store(cout)
+    src = _grid(H, W, kin, dtype, g)
+    src.buf[..., cin:] = 0
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    if mode == "3x3":
+        w, m, s = PK.pack_conv3x3(wt, dtype), L.CONV3X3, 1
+    elif mode == "1x1":
+        w, m, s = PK.pack_conv1x1(wt[:, :, :1, :1].contiguous(), dtype), L.CONV1X1, 1
+    else:
+        w, m, s = PK.pack_upconv(wt, dtype), L.UPCONV, 2
+    n_pad = w.shape[1]
+    op = ConvOp(mode=m, src=src, w=w, k=kin, bias=PK.pad_vec(0.1 * torch.randn(cout, generator=g), n_pad), impl=impl,
+                name=f"{mode}_{cin}_{cout}")
+    oh, ow = s * H, s * W
+    op.out_h, op.out_w, op.out_c = oh, ow, kout
+    if "img" in ex:
+        op.img_c, op.img_layout, op.patch = cout, ex["img"], ex.get("patch", 0)
+        if ex["img"] == L.IMG_MERGED:
+            op.out_img = torch.zeros(1, cout, oh, ow)
+        else:
+            P = ex["patch"]
+            op.out_img = torch.zeros((oh // P) * (ow // P), cout, P, P)
+        return op
+    if ex.get("raw"):
+        op.out_raw = Grid(torch.full((oh + 2, ow + 2, kout), 7.0).to(dtype), oh, ow, kout)
+    if ex.get("act"):
+        op.out_act = Grid(torch.full((oh + 2, ow + 2, kout), 7.0).to(dtype), oh, ow, kout)
+        if not ex.get("relu"):
+            op.scale = PK.pad_vec(1 + 0.1 * torch.randn(cout, generator=g), n_pad)
+            op.shift = PK.pad_vec(0.1 * torch.randn(cout, generator=g), n_pad)
+            op.leak = 0.02
+        op.border = ex.get("border", L.BORDER_NONE)
+    if "res" in ex:
+        sh = ex["res"]
+        rh, rw = (oh + (1 << sh) - 1) >> sh, (ow + (1 << sh) - 1) >> sh
+        r = _grid(rh, rw, kout, dtype, g)
+        op.res_kind, op.res, op.res_shift, op.res_c, op.res_h, op.res_w = L.RES_GRID, r.buf, sh, kout, rh, rw
+    return op
+
+
+def _conv_to_dev(op: ConvOp) -> ConvOp:
+    import copy
+    d = copy.copy(op)
+    mv = lambda t: None if t is None else t.clone().cuda()
+    mg = lambda g: None if g is None else Grid(g.buf.clone().cuda(), g.h, g.w, g.c)
+    d.src, d.w, d.bias, d.scale, d.shift = mg(op.src), mv(op.w), mv(op.bias), mv(op.scale), mv(op.shift)
+    d.out_raw, d.out_act, d.out_img, d.res = mg(op.out_raw), mg(op.out_act), mv(op.out_img), mv(op.res)
+    d.mod_x, d.mod_mean, d.mod_rstd = mg(op.mod_x), mv(op.mod_mean), mv(op.mod_rstd)
+    return d
+
+
+def _check_conv(opc: ConvOp, opg: ConvOp, dtype):
+    if opc.out_img is not None:
+        err = (opg.out_img.cpu() - opc.out_img).abs().max().item()
+        assert err <= (1e-5 if dtype == torch.float32 else REL[dtype] * 4), f"{opc.name}: image max-abs {err:.3e}"
+        return
+    bordered = opc.border != L.BORDER_NONE
+    if opc.out_raw is not None:
+        _cmp(opc.name + ".raw", opg.out_raw.interior, opc.out_raw.interior, dtype)
+    if opc.out_act is not None:
+        a, b = (opg.out_act.buf, opc.out_act.buf) if bordered else (opg.out_act.interior, opc.out_act.interior)
+        _cmp(opc.name + ".act", a, b, dtype)
+
+
+@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA),
+                                            ("bf16", L.IMPL_UMMA)])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}")
+def test_conv_matches_emulator(be, case, precision, impl):
+    mode, H, W, cin, cout, ex = case
+    dtype = DT[precision]
+    opc = _make_conv(mode, H, W, cin, cout, ex, dtype, impl, seed=H * 1000 + W * 10 + cin + cout)
+    opg = _run_both(be, opc, _conv_to_dev)
+    _check_conv(opc, opg, dtype)
+
+
+@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA), ("bf16", L.IMPL_UMMA)])
+@pytest.mark.parametrize("C,shift,linear", [(52, 1, False), (26, 0, False), (104, 1, True), (8, 0, False)])
+def test_ssm_embed_conv_matches_emulator(be, precision, impl, C, shift, linear):
+    """The SSM pair: valid conv on a window of the hidden map + modulation epilogue (layers.py:228-234)."""
+    dtype = DT[precision]
+    g = torch.Generator().manual_seed(C * 7 + shift)
+    H, W = 22, 36
+    cs = c_store(C)
+    m1 = _grid(H + 2, W + 2, 128, dtype, g)                       # interior (H+2)x(W+2): the valid conv's input
+    m1.buf.clamp_(min=0)
+    wt = torch.randn(2 * C, 128, 3, 3, generator=g) / math.sqrt(9 * 128)
+    bias = 0.1 * torch.randn(2 * C, generator=g)
+    w, b = PK.pack_ssm_embed(wt, bias, dtype)
+    xh, xw = (H + shift) >> shift, (W + shift) >> shift
+    x = _grid(xh, xw, cs, dtype, g)
+    x.buf[..., C:] = 0
+    out = Grid(torch.full((H + 2, W + 2, cs), 7.0).to(dtype), H, W, cs)
+    op = ConvOp(mode=L.CONV3X3, src=m1, w=w, k=128, bias=b, impl=impl, name=f"ssm{C}")
+    op.in_h, op.in_w, op.in_pitch, op.in_elem_off = H, W, W + 4, ((W + 4) + 1) * 128
+    op.out_h, op.out_w, op.out_c = H, W, cs
+    op.mod_x, op.mod_shift = x, shift
+    op.mod_mean = PK.pad_vec(0.1 * torch.randn(C, generator=g), cs)
+    op.mod_rstd = PK.pad_vec(1 + 0.2 * torch.rand(C, generator=g), cs)
+    op.out_act, op.leak, op.act_linear = out, 0.02, linear
+    op.border = L.BORDER_NONE if linear else L.BORDER_REPLICATE
+    opg = _run_both(be, op, _conv_to_dev)
+    a, r = (opg.out_act.interior, op.out_act.interior) if linear else (opg.out_act.buf, op.out_act.buf)
+    _cmp(op.name, a, r, dtype)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("C,patch,th,tw", [(104, 16, 2, 3), (16, 16, 3, 2), (128, 16, 1, 2), (32, 8, 2, 2)])
+def test_attention_matches_emulator(be, precision, C, patch, th, tw):
+    dtype = DT[precision]
+    g = torch.Generator().manual_seed(C + patch)
+    xc = c_store(C)
+    x = _grid(th * patch, tw * patch, xc, dtype, g)
+    x.buf[..., C:] = 0
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    kw = dict(w_theta=rnd(C // 8, C) / math.sqrt(C), b_theta=0.1 * rnd(C // 8), w_phi=rnd(C // 8, C) / math.sqrt(C),
+              b_phi=0.1 * rnd(C // 8), w_g=rnd(C // 2, C) / math.sqrt(C), b_g=0.1 * rnd(C // 2),
+              w_o=rnd(C, C // 2) / math.sqrt(C // 2), b_o=0.1 * rnd(C), gamma=torch.tensor([0.7]),
+              scale=PK.pad_vec(1 + 0.1 * rnd(C), xc), shift=PK.pad_vec(0.1 * rnd(C), xc))
+    mk = lambda dev: AttentionOp(
+        x=Grid(x.buf.clone().to(dev), x.h, x.w, xc), th=th, tw=tw, patch=patch, C=C,
+        out_raw=Grid(torch.full_like(x.buf, 7.0).to(dev), x.h, x.w, xc), out_act=Grid(torch.full_like(x.buf, 7.0).to(dev), x.h, x.w, xc),
+        leak=0.02, border=L.BORDER_REPLICATE, **{k: v.to(dev) for k, v in kw.items()})
+    opc, opg = mk("cpu"), mk("cuda")
+    EmulatorBackend().attention(opc)
+    be.attention(opg)
+    torch.cuda.synchronize()
+    _cmp("att.raw", opg.out_raw.interior, opc.out_raw.interior, dtype)
+    _cmp("att.act", opg.out_act.buf, opc.out_act.buf, dtype)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+def test_data_movement_is_bit_exact(be, precision):
+    dtype = DT[precision]
+    g = torch.Generator().manual_seed(3)
+    emu = EmulatorBackend()
+    # pack_nchw (z grid, utils.py:228)
+    src = torch.randn(13, 10, 18, generator=g)
+    dc, dg = torch.full((10, 18, 16), 7.0).to(dtype), torch.full((10, 18, 16), 7.0).to(dtype).cuda()
+    emu.pack_nchw(src, dc)
+    be.pack_nchw(src.cuda(), dg)
+    assert torch.equal(dg.cpu(), dc)
+    # pack_map_taps (SSM noise map, utils.py:246)
+    m = torch.randn(14, 23, generator=g)
+    tc = Grid(torch.zeros(14, 23, 16).to(dtype), 12, 21, 16)
+    tg = Grid(torch.zeros(14, 23, 16).to(dtype).cuda(), 12, 21, 16)
+    emu.pack_map_taps(m, tc)
+    be.pack_map_taps(m.cuda(), tg)
+    assert torch.equal(tg.interior.cpu(), tc.interior)
+    # copy_rect / fill_frame (halo moves, F.pad of layers.py:82)
+    a = _grid(9, 11, 24, dtype, g)
+    for border in (L.BORDER_REPLICATE, L.BORDER_CONSTANT):
+        for sides in (15, 1, 2, 4, 8, 5, 10):
+            c, d = _clone_grid(a, "cpu"), _clone_grid(a, "cuda")
+            emu.fill_frame(c, border, sides)
+            be.fill_frame(d, border, sides)
+            assert torch.equal(d.buf.cpu(), c.buf), (border, sides)
+    dst_c, dst_g = torch.zeros(5, 30, 24).to(dtype), torch.zeros(5, 30, 24).to(dtype).cuda()
+    emu.copy_rect(a.buf, 2, 3, dst_c, 1, 4, 3, 7)
+    be.copy_rect(a.buf.cuda(), 2, 3, dst_g, 1, 4, 3, 7)
+    assert torch.equal(dst_g.cpu(), dst_c)
+
+
+def test_bad_arguments_raise(be):
+    """Errors come back as ItgError with the library's message, not as crashes."""
+    g = torch.Generator().manual_seed(1)
+    op = _conv_to_dev(_make_conv("3x3", 8, 8, 16, 16, dict(raw=True), torch.float16, L.IMPL_UMMA, 1))
+    op.out_h = 9
+    with pytest.raises(L.ItgError, match="does not match"):
+        be.conv(op)
+    with pytest.raises(L.ItgError, match="CUDA tensors"):
+        L.ptr(torch.zeros(4))

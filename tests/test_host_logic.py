@@ -1,0 +1,139 @@
+"""CPU tests of the host side: launch plans (engine.py), weight packing (packing.py), the sequential halo state
+machine (halo.py), the sampler geometry (utils.py) and the C-ABI symbol table.  The CUDA kernels are replaced by
+tests/emulator.py (fp32 torch restatement of each launch); results are held to the reference's golden outputs."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+import infinite_texture_gans_b200 as itg
+from common import CASES, compare_with_golden, load_case, make_generator
+from emulator import EmulatorBackend
+from infinite_texture_gans_b200 import _lib as L
+from infinite_texture_gans_b200.config import GenConfig, flops_per_patch
+from oracle import itg_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_plan_oneshot_matches_reference(name):
+    d, kw, ocfg, sd, z, maps = load_case(name)
+    net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
+    img = itg.utils.generate_full_grid(net, z, maps)
+    compare_with_golden(d, "one", img, 5e-5)
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "241" not in c])
+def test_sequential_protocol_matches_reference(name):
+    """image_location state machine on device buffers == LocalPadder's (layers.py:78-143), gamma != 0 included."""
+    d, kw, ocfg, sd, z, maps = load_case(name)
+    net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
+    H, W = int(d["H"]), int(d["W"])
+    img = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], output_resolution_height=H,
+                                                      output_resolution_width=W, schedule="sequential", noise=(z, maps))
+    compare_with_golden(d, "seq", img, 5e-5)
+
+
+def test_reference_style_map_crops_are_accepted():
+    """forward() takes the per-patch (nph*npw,1,r+4,r+4) map crops the reference sampler builds (utils.py:345-351)."""
+    d, kw, ocfg, sd, z, maps = load_case("gen_ssm4_att_rep")
+    th, tw = int(d["total_h"]), int(d["total_w"])
+    net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
+    itg.LocalPadder.set_attributes(num_patches_h=th, num_patches_w=tw)
+    try:
+        crops = [itg.utils.crop_images(m, 4 * 2 ** i + 4, 4 * 2 ** i + 4, 4 * 2 ** i) for i, m in enumerate(maps)]
+        patches = net(z, crops)
+    finally:
+        itg.LocalPadder.set_attributes()
+    compare_with_golden(d, "one", itg.utils.merge_patches_into_image(patches, th, tw), 5e-5)
+
+
+def test_inter_location_without_state_raises():
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
+    net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
+    with pytest.raises(RuntimeError, match="1st_row_1st_col"):
+        net(torch.zeros(1, kw["z_dim"], 14, 14), None, "inter_row_inter_col")
+
+
+def test_seeded_sampler_draws_reference_noise():
+    """Same torch seed -> same z / maps as the reference draw order (utils.py:228, 246)."""
+    torch.manual_seed(5)
+    z, maps = itg.utils.draw_noise(1, 16, 4, 4, 1, "SSM", 3, 5)
+    torch.manual_seed(5)
+    z2 = torch.randn(1, 16, 14, 22)
+    m2 = [torch.randn(1, 1, 3 * 4 * 2 ** i + 4, 5 * 4 * 2 ** i + 4) for i in range(4)]
+    assert torch.equal(z, z2) and all(torch.equal(a, b) for a, b in zip(maps, m2))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(33, 3000), st.integers(33, 3000), st.sampled_from([4, 5, 6]), st.sampled_from([2, 3, 4]))
+def test_geometry_matches_oracle(H, W, n, nps):
+    cfg = O.GenCfg(n_layers_G=n, num_patches_h=nps, num_patches_w=nps)
+    if H <= cfg.patch_px or W <= cfg.patch_px:
+        return
+    g = itg.utils.patch_grid_geometry(H, W, n, 4, nps, nps)
+    assert g == O.geometry(H, W, cfg)
+    assert g["total_h"] * g["P"] >= H and g["total_w"] * g["P"] >= W
+
+
+def test_crop_and_merge_match_oracle():
+    x = torch.arange(2 * 3 * 14 * 22, dtype=torch.float32).reshape(2, 3, 14, 22)
+    assert torch.equal(itg.utils.crop_images(x, 6, 6, 4), O.crop_windows(x, 6, 6, 4))
+    p = torch.arange(12 * 2 * 4 * 4, dtype=torch.float32).reshape(12, 2, 4, 4)
+    assert torch.equal(itg.utils.merge_patches_into_image(p, 2, 3), O.merge_patches(p, 2, 3))
+
+
+def test_flop_model_matches_survey():
+    f = lambda **k: flops_per_patch(GenConfig(z_dim=128, G_ch=52, **k)) / 1e6
+    assert abs(f(n_layers_G=6) - 938.55) < 0.01
+    assert abs(f(n_layers_G=4) - 608.73) < 0.01
+    assert abs(f(n_layers_G=5, type_norm="SSM") - 5475.37) < 0.01
+
+
+def test_buffer_reuse_does_not_change_results():
+    from infinite_texture_gans_b200.engine import Engine, Plan
+    d, kw, ocfg, sd, z, maps = load_case("gen_ssm4_att_rep")
+    th, tw = int(d["total_h"]), int(d["total_w"])
+    eng = Engine(GenConfig(**kw), sd, "fp32", "cpu", backend=EmulatorBackend())
+    outs = []
+    for reuse in (True, False):
+        p = Plan(eng.cfg, eng.weights, eng.backend, th, tw, eng.device, eng.impl, reuse_buffers=reuse)
+        p.set_inputs(z, [m[0, 0] for m in maps])
+        outs.append((p.run().clone(), p.arena_bytes))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][1] < outs[1][1]
+
+
+def test_library_exports_every_declared_symbol():
+    """include/itg.h <-> libitg_b200.so <-> the ctypes binding agree (no compute calls: runs without a GPU)."""
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    header = open(os.path.join(ROOT, "include", "itg.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(itg_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(L.EXPORTS)
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    lib2 = L.load()
+    assert lib2.itg_version() == 1
+    assert lib2.itg_conv_desc_size() == ctypes.sizeof(L.ConvDesc)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libitg_b200.so")
+    with pytest.raises(L.ItgError, match="no CPU or PyTorch fallback"):
+        L.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "infinite_texture_gans_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("Oracle", ""), f
