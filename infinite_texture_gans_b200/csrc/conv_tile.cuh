@@ -1,0 +1,324 @@
+// Persistent "halo-tile" implicit-GEMM convolution for the thin layers of the Generator (K <= 64 channels per
+// tap, N <= 64 GEMM columns: blocks 4-6 and the final conv of the 241 config, 52.6 % of its FLOPs).
+//
+// Those layers are bound by data movement and per-pixel epilogue work, not by the tensor pipe, so the kernel is
+// organised around bytes and instruction counts:
+//   * the weights of ALL taps (<= 72 KB) are parked in shared memory once per CTA for the whole launch;
+//   * each 16 x 8 output tile loads its (16+2) x (8+2) input neighbourhood ONCE, as K/8 planes of
+//     [pixel][8 channels] -- the nine taps of the 3x3 window (or the 4 x 4 phase taps of the folded nearest-2x
+//     up-sampling) are nine shifted views of that one tile: the local-padding halo gather is a 16-byte-granular
+//     offset in the MMA's shared-memory descriptor (no-swizzle K-major layout, 8 x 16 B core matrices: rows =
+//     8 consecutive pixels of a tile row, SBO = one halo-tile row, LBO = one plane).  The planes are filled by
+//     three producer warps with 16-byte cp.async (zero-fill outside the buffer), several tiles in flight;
+//   * CTAs are persistent (grid = SM count): producer warps, the MMA warp and two groups of epilogue warps run
+//     as a pipeline over the tile sequence (multi-stage input ring, double-buffered TMEM accumulators), so the
+//     epilogue of tile i overlaps the loads and MMAs of tiles i+1, i+2;
+//   * the MMA warp runs warp-uniform (descriptors live in uniform registers, one elected lane issues), the conv
+//     mode and the epilogue variant are template parameters: measured on B200, the single-thread issue loop of
+//     the first version cost ~320 cycles per tcgen05.mma and was the bottleneck (profiles/r01_notes.md).
+#pragma once
+#include "conv_umma.cuh"
+
+namespace itg {
+
+constexpr int TILE_W = 8, TILE_H = 16;                       // output tile = 128 GEMM rows
+constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;      // input neighbourhood
+constexpr int HALO_PX = HALO_W * HALO_H;                     // 180
+constexpr int PLANE_BYTES = HALO_PX * 16;                    // one 8-channel plane of the halo tile: 2880 B
+constexpr int TILE_THREADS = 416;          // warps 0,2,12: producers; 1,3: MMA issuers; 4..11: two epilogue groups
+constexpr int TILE_HDR_BYTES = 1024;       // barriers + per-channel epilogue vectors
+constexpr int TILE_MAX_STAGES = 8;
+constexpr int TILE_PWARPS = 3;              // producer warps 0, 2, 3: each loads every third tile on its own
+
+struct TileParams {
+  int m_h, m_w;            // M-grid size (input interior)
+  int tiles_x, ntiles;
+  const void* in;          // framed grid tensor (buffer origin)
+  int in_c, in_pitch;      // storage channels, pixels per buffer row
+  int buf_h, buf_w;        // buffer extent in pixels (interior + frame)
+  int in_cg_off;           // first 8-channel group of the input slice
+  int kg;                  // 8-channel planes per tile (k_pad / 8): 2, 4 or 8
+  int n;                   // GEMM columns (n_pad), multiple of 16, <= 64
+  int n_src, k_src;        // row pitch / K pitch of the [tap][n_pad][k_pad] weight tensor in global memory
+  int taps_w;              // taps in the weight tensor: 9 | 1 | 16
+  int w_bytes;             // bytes of the shared-memory weight image
+  int stage_bytes;         // bytes of one input stage (kg planes)
+  int stages, ahead;       // input ring depth; tiles a producer WARP keeps in flight before publishing (1 or 2)
+  int nbuf;                // TMEM accumulator buffers (2 or 4)
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  const void* w;
+  unsigned long long* dbg;  // optional [grid][16] cycle counters (ITG_TILE_DBG=1), NULL in production
+  EpiParams ep;
+};
+
+// timeline trace of CTA 0, tiles 40..47: trace[(it - 40) * 16 + slot] = clock
+#define ITG_TRACE(itv, slot) do { if (p.dbg && blockIdx.x == 0 && (itv) >= 40 && (itv) < 48) p.dbg[4096 + ((itv) - 40) * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+#define ITG_ACC(slot, tvar) do { if (p.dbg) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tvar); tvar = now_; } } while (0)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {        // wait until at most n groups are pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+// K-major operand without swizzle (8 x 16 B core matrices).  lo word: start address >> 4 | LBO >> 4 << 16
+// (LBO = bytes between the two K halves of one MMA); hi word: SBO >> 4 (bytes between 8-row groups) | version.
+__device__ __forceinline__ uint64_t desc_noswz(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
+  const uint32_t lo = (addr16 & 0x3FFFu) | (lbo16 << 16);
+  const uint32_t hi = sbo16 | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+template <int MODE> struct TileMode;
+template <> struct TileMode<ITG_CONV3X3> { static constexpr int NPHASE = 1, NTAPS = 9; };
+template <> struct TileMode<ITG_CONV1X1> { static constexpr int NPHASE = 1, NTAPS = 1; };
+template <> struct TileMode<ITG_UPCONV> { static constexpr int NPHASE = 4, NTAPS = 4; };
+
+// All MMAs of one tile: NPHASE accumulators x NTAPS taps x KSTEPS 16-channel steps, fully unrolled.
+template <int MODE, int KSTEPS>
+__device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w16, uint32_t n16, uint32_t kg, uint32_t idesc) {
+#pragma unroll
+  for (int q = 0; q < TileMode<MODE>::NPHASE; ++q) {
+#pragma unroll
+    for (int t = 0; t < TileMode<MODE>::NTAPS; ++t) {
+      int dy, dx, wt;
+      tap_offsets(MODE, q, t, dy, dx, wt);
+      const uint32_t shift16 = (uint32_t)((1 + dy) * HALO_W + (1 + dx));
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t adesc = desc_noswz(a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16) + shift16, PLANE_BYTES / 16, HALO_W);
+        const uint64_t bdesc = desc_noswz(w16 + ((uint32_t)wt * kg + (uint32_t)(2 * ks)) * n16, n16, 8);
+        umma_f16(d0 + (uint32_t)q * n16, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+      }
+    }
+  }
+}
+
+template <typename T, int F, int MODE>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+conv_tile_kernel(const TileParams p) {
+  constexpr int NPHASE = TileMode<MODE>::NPHASE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_full = sbase;                    // [stages]
+  const uint32_t bar_empty = sbase + 64;              // [stages]
+  const uint32_t bar_tfull = sbase + 128;             // [nbuf <= 4] accumulator buffer complete
+  const uint32_t bar_tempty = sbase + 160;            // [nbuf <= 4] accumulator buffer drained
+  const uint32_t tmem_slot = sbase + 192;
+  float* vec = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + 256);   // bias | scale | shift, 64 floats each
+  const uint32_t w_smem = sbase + TILE_HDR_BYTES;
+  const uint32_t a_smem = w_smem + (uint32_t)p.w_bytes;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(bar_full + 8 * i, 32);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < p.nbuf; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);               // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+
+  // ---- park the weights of every tap in shared memory: image [tap][k-group][n][8 channels] ----
+  {
+    const T* wg = reinterpret_cast<const T*>(p.w);
+    const int chunks = p.taps_w * p.kg * p.n;                                  // 16-byte chunks
+    for (int i = threadIdx.x; i < chunks; i += TILE_THREADS) {
+      const int nn = i % p.n, j = (i / p.n) % p.kg, t = i / (p.n * p.kg);
+      const uint4 v = *reinterpret_cast<const uint4*>(wg + ((size_t)t * p.n_src + nn) * p.k_src + j * 8);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(w_smem + (uint32_t)i * 16u), "r"(v.x), "r"(v.y),
+                   "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+    fence_proxy_async();                                                       // generic writes -> async proxy (UMMA) reads
+    if (threadIdx.x < 64) {
+      const int i = threadIdx.x;
+      vec[i] = (p.ep.bias != nullptr && i < p.n) ? p.ep.bias[i] : 0.f;
+      vec[64 + i] = (p.ep.scale != nullptr && i < p.n) ? p.ep.scale[i] : 1.f;
+      vec[128 + i] = (p.ep.shift != nullptr && i < p.n) ? p.ep.shift[i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 || warp == 2 || warp == 12) {                                  // ---- producers ----
+    const int pw = warp == 0 ? 0 : (warp == 2 ? 1 : 2);            // producer warp 0..2 loads tiles it = 3k + pw, all 32 lanes on one tile
+    const int kg_log2 = 31 - __clz(p.kg);
+    const int cg_total = p.in_c >> 3;
+    const T* in = reinterpret_cast<const T*>(p.in);
+    // 32 % kg == 0: a lane always serves the same 8-channel plane j and walks the halo pixels with a fixed stride
+    const int j = lane & (p.kg - 1), px0 = lane >> kg_log2, px_step = 32 >> kg_log2;
+    const bool cg_ok = (p.in_cg_off + j) < cg_total;
+    const uint32_t ch_off = (uint32_t)((p.in_cg_off + j) * 8);
+    const uint32_t plane_off = (uint32_t)(j * PLANE_BYTES);
+    unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    int k = 0;
+    for (int it = pw; blockIdx.x + it * (int)gridDim.x < p.ntiles; it += TILE_PWARPS, ++k) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;   // halo origin in buffer pixels
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      ITG_ACC(0, tl);
+      const uint32_t dst0 = a_smem + (uint32_t)(s * p.stage_bytes) + plane_off;
+      const T* src0 = in + ((size_t)y0 * p.in_pitch + x0) * (size_t)p.in_c + ch_off;
+      const bool inside = cg_ok && (y0 + HALO_H <= p.buf_h) && (x0 + HALO_W <= p.buf_w);
+      if (inside) {
+#pragma unroll 4
+        for (int px = px0; px < HALO_PX; px += px_step) {
+          const int hy = (px * 205) >> 11, hx = px - hy * HALO_W;
+          cp_async16(dst0 + (uint32_t)(px * 16), src0 + (uint32_t)((hy * p.in_pitch + hx) * p.in_c));
+        }
+      } else {
+        for (int px = px0; px < HALO_PX; px += px_step) {
+          const int hy = (px * 205) >> 11, hx = px - hy * HALO_W;
+          const bool valid = cg_ok && (y0 + hy < p.buf_h) && (x0 + hx < p.buf_w);
+          cp_async16_zfill(dst0 + (uint32_t)(px * 16), valid ? src0 + (uint32_t)((hy * p.in_pitch + hx) * p.in_c) : in, valid);
+        }
+      }
+      cp_async_commit();
+      ITG_ACC(1, tl);
+      if (k >= p.ahead) {                                // this warp's tile (k - ahead) has landed: publish it to the MMA warp
+        cp_async_wait_dyn(p.ahead);
+        ITG_ACC(2, tl);
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * ((it - p.ahead * TILE_PWARPS) % p.stages));
+        ITG_ACC(3, tl);
+      }
+    }
+    cp_async_wait_dyn(0);
+    fence_proxy_async();
+    for (int q = (k > p.ahead ? k - p.ahead : 0); q < k; ++q) mbar_arrive(bar_full + 8 * ((q * TILE_PWARPS + pw) % p.stages));
+    if (p.dbg && pw == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_acc[i];
+  } else if (warp == 1 || warp == 3) {                                         // ---- two MMA warps (uniform; one lane issues), alternate tiles ----
+    const int mw = warp >> 1;
+    unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    const int ksteps = p.kg >> 1;
+    const uint32_t w16 = w_smem >> 4, n16 = (uint32_t)p.n;                     // weight image: 16 B per (k-group, n)
+    int it = mw;
+    for (int tile = blockIdx.x + mw * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      const int b = it & (p.nbuf - 1);
+      const uint32_t bph = (uint32_t)(it / p.nbuf) & 1u;
+      if (lane == 0) ITG_TRACE(it, 0);
+      mbar_wait(bar_tempty + 8 * b, bph ^ 1u);                                 // epilogue has drained this accumulator
+      if (lane == 0) ITG_TRACE(it, 1);
+      if (p.dbg && it >= p.nbuf && clock64() - tl > 200) {                    // really blocked: how old is the arrival that released us?
+        dbg_acc[3] += (unsigned long long)(clock64() - reinterpret_cast<volatile long long*>(vec + 192)[4 + b]);
+      }
+      ITG_ACC(0, tl);
+      mbar_wait(bar_full + 8 * s, ph);
+      if (lane == 0) ITG_TRACE(it, 2);
+      ITG_ACC(1, tl);
+      tc_fence_after();
+      const uint32_t a16 = (a_smem + (uint32_t)(s * p.stage_bytes)) >> 4;
+      if (elect_one_sync()) {                                                        // one lane issues the whole tile, straight-line
+        const uint32_t d0 = tmem_base + (uint32_t)(b * NPHASE * p.n);
+        if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        umma_commit(bar_empty + 8 * s);                                        // input stage may be refilled
+        umma_commit(bar_tfull + 8 * b);                                        // accumulators of this tile complete
+        if (p.dbg) reinterpret_cast<volatile long long*>(vec + 192)[b] = clock64();
+      }
+      __syncwarp();
+      if (lane == 0) ITG_TRACE(it, 3);
+      ITG_ACC(2, tl);
+    }
+    if (p.dbg && lane == 0 && mw == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i];
+  } else if (warp >= 4 && warp < 12) {                                         // ---- epilogue ----
+    // two groups of four warps; group g drains every second tile of this CTA (accumulator buffer it % nbuf)
+    const int g = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    EpiParams ep = p.ep;
+    if (ep.bias != nullptr) ep.bias = vec;
+    if (ep.scale != nullptr) { ep.scale = vec + 64; ep.shift = vec + 128; }
+    unsigned long long dbg_acc[4] = {0, 0, 0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
+      const int b = it & (p.nbuf - 1);
+      const uint32_t bph = (uint32_t)(it / p.nbuf) & 1u;
+      const int y = (tile / p.tiles_x) * TILE_H + (row >> 3), x = (tile % p.tiles_x) * TILE_W + (row & 7);
+      const bool valid = (y < p.m_h) && (x < p.m_w);
+      // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier
+      uint4 pre[8];
+      constexpr bool PRE = (F & EF_GENERIC) == 0 && (F & EF_RES) != 0 && NPHASE == 1;
+      if (PRE && valid) {
+        const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(y >> ep.res_shift, x >> ep.res_shift, ep.res_w, ep.res_c, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 8 < p.n && i * 8 < ep.out_c) pre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+      }
+      if (lane == 0) ITG_TRACE(it, 4 + ew * 3);
+      mbar_wait(bar_tfull + 8 * b, bph);
+      if (lane == 0) ITG_TRACE(it, 5 + ew * 3);
+      if (p.dbg) dbg_acc[2] += (unsigned long long)(clock64() - reinterpret_cast<volatile long long*>(vec + 192)[b]);
+      ITG_ACC(0, tl);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < NPHASE; ++q) {
+        int oy = y, ox = x;
+        if (MODE == ITG_UPCONV) { oy = 2 * y + (q >> 1); ox = 2 * x + (q & 1); }
+        const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * NPHASE + q) * p.n);
+        for (int c0 = 0; c0 < p.n; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c0, v);
+          if (valid) {
+            float a[8], c[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = v[i]; c[i] = v[8 + i]; }
+            epilogue8<T, F>(ep, oy, ox, c0, a, PRE ? &pre[(c0 >> 3) & 7] : nullptr);
+            epilogue8<T, F>(ep, oy, ox, c0 + 8, c, PRE ? &pre[((c0 >> 3) + 1) & 7] : nullptr);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (p.dbg && ew == 3 && lane == 0) reinterpret_cast<volatile long long*>(vec + 192)[4 + b] = clock64();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+      if (lane == 0) ITG_TRACE(it, 6 + ew * 3);
+      ITG_ACC(1, tl);
+    }
+    if (p.dbg && ew == 0 && lane == 0) {
+      for (int i = 0; i < 2; ++i) p.dbg[blockIdx.x * 16 + 8 + g * 2 + i] = dbg_acc[i];
+      p.dbg[blockIdx.x * 16 + 12 + g] = dbg_acc[2];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace itg

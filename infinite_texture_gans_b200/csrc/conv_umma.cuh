@@ -89,6 +89,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -201,26 +206,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {                                                   // ---- MMA issuer ----
-      int it = 0;
-      for (int t = 0; t < ntaps; ++t) {
-        for (int c = 0; c < p.nchunks; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = stage0 + s * stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
-          const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
-          const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
-          for (int k = 0; k < nk; ++k)          // +32 B (16 channels) per K step inside the swizzle row
-            umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+  } else if (warp == 1) {                                                  // ---- MMA warp: uniform control flow, one elected lane issues ----
+    int it = 0;
+    for (int t = 0; t < ntaps; ++t) {
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = stage0 + s * stage_bytes;
+        const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
+        const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
+        const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
+        if (elect_one_sync()) {                 // +32 B (16 channels) per K step inside the swizzle row
+          umma_f16(tmem_base, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u);
+          if (nk > 1) umma_f16(tmem_base, adesc + 2, bdesc + 2, p.idesc, 1u);
+          if (nk > 2) umma_f16(tmem_base, adesc + 4, bdesc + 4, p.idesc, 1u);
+          if (nk > 3) umma_f16(tmem_base, adesc + 6, bdesc + 6, p.idesc, 1u);
           umma_commit(bar_empty + 8 * s);       // frees the stage when these MMAs have read it
         }
+        __syncwarp();
       }
-      umma_commit(bar_acc);                      // accumulator complete
     }
+    if (elect_one_sync()) umma_commit(bar_acc);  // accumulator complete
     __syncwarp();
   } else if (warp >= 4) {                                                // ---- epilogue ----
     const int ew = warp & 3;

