@@ -4,7 +4,10 @@
 // of the patch, i.e. 32 queries AND eight complete 2x2 pooling windows, so everything except the pooled keys / values
 // stays in that warp's registers (flash-attention style chaining of m16n8k16 accumulators into the next A operand):
 //
-//   [theta | phi | g] = X Wqkv^T + b      256 x 96 x C      (theta 16 cols, phi 16, g 64; zero padded)
+//   [theta | phi | g] = X Wqkv^T + b      256 x 96 x C      (theta 16 cols, phi 16, g 64; zero padded).  The scores are
+//                                         exponentiated, so theta / phi keep ~fp32 accuracy: their weights, and then
+//                                         theta / phi themselves, are carried as hi + lo pairs of the 16-bit type
+//                                         (W_hi X + W_lo X;  S = th_hi ph_hi + th_hi ph_lo + th_lo ph_hi)
 //   phi_p, g_p = maxpool2x2(phi), maxpool2x2(g)             in-register max + one shuffle, parked in shared memory
 //   S = theta phi_p^T                     256 x 64 x 16     no 1/sqrt(d) scaling in the reference
 //   P = softmax_rows(S)                   fp32, in registers
@@ -33,12 +36,12 @@ struct AttnMmaParams {
 };
 
 constexpr int AM_PATCH = 16, AM_NPX = 256, AM_NPOOL = 64;
-constexpr int AM_QKV = 96;                 // 16 theta + 16 phi + 64 g columns
+constexpr int AM_QKV = 128;                // 16 theta + 16 phi + 64 g columns + 32 low-order halves of the theta / phi weights
 constexpr int AM_KMAX = 128;               // max channels
 constexpr int AM_XP = AM_KMAX + 8;         // row pitch (elements) of the x / Wqkv tiles: +16 B keeps LDS.32 fragment loads conflict-free
 constexpr int AM_OP = 64 + 8;              // row pitch of Wo / g_p^T tiles (K = 64)
 constexpr int AM_PP = 16 + 8;              // row pitch of phi_p
-constexpr int AM_SMEM = (AM_NPX * AM_XP + AM_QKV * AM_XP + AM_KMAX * AM_OP + AM_NPOOL * AM_PP + 64 * AM_OP) * 2 + (AM_QKV + AM_KMAX) * 4;
+constexpr int AM_SMEM = (AM_NPX * AM_XP + AM_QKV * AM_XP + AM_KMAX * AM_OP + 2 * AM_NPOOL * AM_PP + 64 * AM_OP) * 2 + (AM_QKV + AM_KMAX) * 4;
 
 template <typename T> struct Pack2;
 template <> struct Pack2<__half> {
@@ -69,8 +72,8 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
   T* Xs = reinterpret_cast<T*>(am_smem);                 // [256][AM_XP]   x tile, later out_raw in place
   T* Wq = Xs + AM_NPX * AM_XP;                           // [96][AM_XP]    theta | phi | g weights
   T* Wo = Wq + AM_QKV * AM_XP;                           // [128][AM_OP]   output 1x1 weights (K = C/2 padded to 64)
-  T* Pp = Wo + AM_KMAX * AM_OP;                          // [64][AM_PP]    pooled phi  [key j][channel]
-  T* Gt = Pp + AM_NPOOL * AM_PP;                         // [64][AM_OP]    pooled g, transposed [channel][key j]
+  T* Pp = Wo + AM_KMAX * AM_OP;                          // [2][64][AM_PP] pooled phi  [hi | lo][key j][channel]
+  T* Gt = Pp + 2 * AM_NPOOL * AM_PP;                     // [64][AM_OP]    pooled g, transposed [channel][key j]
   float* bq = reinterpret_cast<float*>(Gt + 64 * AM_OP); // [96]
   float* bo = bq + AM_QKV;                               // [128]
 
@@ -98,12 +101,14 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
     for (int i = threadIdx.x; i < AM_QKV * kpad; i += 256) {
       const int n = i / kpad, k = i % kpad;
       float v = 0.f;
+      const int nn = n >= 96 ? n - 96 : n;               // rows 96..127: low-order halves of rows 0..31
       if (k < C) {
-        if (n < 16) { if (n < C8) v = p.w_theta[n * C + k]; }
-        else if (n < 32) { if (n - 16 < C8) v = p.w_phi[(n - 16) * C + k]; }
-        else if (n - 32 < C2) v = p.w_g[(n - 32) * C + k];
+        if (nn < 16) { if (nn < C8) v = p.w_theta[nn * C + k]; }
+        else if (nn < 32) { if (nn - 16 < C8) v = p.w_phi[(nn - 16) * C + k]; }
+        else if (nn - 32 < C2) v = p.w_g[(nn - 32) * C + k];
       }
-      Wq[n * AM_XP + k] = Op<T>::from_f(v);
+      const T hi = Op<T>::from_f(v);
+      Wq[n * AM_XP + k] = n >= 96 ? Op<T>::from_f(v - Op<T>::to_f(hi)) : hi;
     }
     for (int i = threadIdx.x; i < NT_OUT * 8 * 64; i += 256) {
       const int n = i >> 6, k = i & 63;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
       float v = 0.f;
       if (i < 16) { if (i < C8) v = p.b_theta[i]; }
       else if (i < 32) { if (i - 16 < C8) v = p.b_phi[i - 16]; }
-      else if (i - 32 < C2) v = p.b_g[i - 32];
+      else if (i < 96 && i - 32 < C2) v = p.b_g[i - 32];
       bq[i] = v;
     }
     for (int i = threadIdx.x; i < AM_KMAX; i += 256) bo[i] = i < C ? p.b_o[i] : 0.f;
@@ -121,72 +126,123 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
   __syncthreads();
 
   const int row0 = warp * 32;                            // this warp's first pixel
-  // ---------------- 1. [theta | phi | g] = X Wqkv^T ----------------
-  float acc[2][12][4];
+  // ---------------- 1. [theta | phi | g] = X Wqkv^T, 2. 2x2 max pooling ----------------
+  // Pooling: m = 0 / 1 are the patch rows 2w / 2w+1 (same px); fragment rows gr, gr^1 are px pairs -> one shuffle
+  // across lanes ^4; lanes with even gr then own window jx = gr/2 (c0,c1) and jx + 4 (c2,c3) of window row jy = w.
+  uint32_t th_hi[2][4], th_lo[2][4];                     // theta as A operand of the score GEMM, hi + lo
+  {
+    // pass A: theta (tiles 0,1), phi (2,3) with hi weights, plus the same four tiles with the lo weights (rows 96..127)
+    float acc[2][8][4];
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int n = 0; n < 12; ++n)
+      for (int n = 0; n < 8; ++n)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
-  for (int kt = 0; kt < KT; ++kt) {
-    uint32_t a[2][4];
+        for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const T* xr = Xs + (row0 + m * 16 + gr) * AM_XP + kt * 16 + gc;
+        a[m][0] = *reinterpret_cast<const uint32_t*>(xr);
+        a[m][1] = *reinterpret_cast<const uint32_t*>(xr + 8 * AM_XP);
+        a[m][2] = *reinterpret_cast<const uint32_t*>(xr + 8);
+        a[m][3] = *reinterpret_cast<const uint32_t*>(xr + 8 * AM_XP + 8);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int wrow = (n < 4 ? n * 8 : 96 + (n - 4) * 8) + gr;
+        const T* wr = Wq + wrow * AM_XP + kt * 16 + gc;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+        mma16816<T>(acc[0][n], a[0], b0, b1);
+        mma16816<T>(acc[1][n], a[1], b0, b1);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {                        // full-precision theta / phi = hi part + lo part + bias
+      const float b0 = bq[n * 8 + gc], b1 = bq[n * 8 + gc + 1];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        acc[m][n][0] += acc[m][n + 4][0] + b0; acc[m][n][1] += acc[m][n + 4][1] + b1;
+        acc[m][n][2] += acc[m][n + 4][2] + b0; acc[m][n][3] += acc[m][n + 4][3] + b1;
+      }
+    }
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-      const T* xr = Xs + (row0 + m * 16 + gr) * AM_XP + kt * 16 + gc;
-      a[m][0] = *reinterpret_cast<const uint32_t*>(xr);
-      a[m][1] = *reinterpret_cast<const uint32_t*>(xr + 8 * AM_XP);
-      a[m][2] = *reinterpret_cast<const uint32_t*>(xr + 8);
-      a[m][3] = *reinterpret_cast<const uint32_t*>(xr + 8 * AM_XP + 8);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {                      // A regs: (tile 0: c0c1, c2c3), (tile 1: c0c1, c2c3)
+        const float v0 = acc[m][r >> 1][(r & 1) * 2], v1 = acc[m][r >> 1][(r & 1) * 2 + 1];
+        const float h0 = Op<T>::to_f(Op<T>::from_f(v0)), h1 = Op<T>::to_f(Op<T>::from_f(v1));
+        th_hi[m][r] = Pack2<T>::pack(h0, h1);
+        th_lo[m][r] = Pack2<T>::pack(v0 - h0, v1 - h1);
+      }
     }
 #pragma unroll
-    for (int n = 0; n < 12; ++n) {
-      const T* wr = Wq + (n * 8 + gr) * AM_XP + kt * 16 + gc;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-      mma16816<T>(acc[0][n], a[0], b0, b1);
-      mma16816<T>(acc[1][n], a[1], b0, b1);
-    }
-  }
+    for (int n = 2; n < 4; ++n) {
+      float v[4];
 #pragma unroll
-  for (int n = 0; n < 12; ++n) {
-    const float b0 = bq[n * 8 + gc], b1 = bq[n * 8 + gc + 1];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) { acc[m][n][0] += b0; acc[m][n][1] += b1; acc[m][n][2] += b0; acc[m][n][3] += b1; }
-  }
-
-  // ---------------- 2. 2x2 max pooling of phi (n 2..3) and g (n 4..11) ----------------
-  // m = 0 / 1 are the patch rows 2w / 2w+1 (same px); fragment rows gr, gr^1 are px pairs -> one shuffle across lanes ^4
-#pragma unroll
-  for (int n = 2; n < 12; ++n) {
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[i] = fmaxf(acc[0][n][i], acc[1][n][i]);
-      v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 4));
-    }
-    if ((gr & 1) == 0) {
-      const int j0 = warp * 8 + (gr >> 1), j1 = j0 + 4;  // window of px rows gr (c0,c1) and gr + 8 (c2,c3)
-      if (n < 4) {
+      for (int i = 0; i < 4; ++i) {
+        v[i] = fmaxf(acc[0][n][i], acc[1][n][i]);
+        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 4));
+      }
+      if ((gr & 1) == 0) {
+        const int j0 = warp * 8 + (gr >> 1), j1 = j0 + 4;
         const int c = (n - 2) * 8 + gc;
-        *reinterpret_cast<uint32_t*>(Pp + j0 * AM_PP + c) = Pack2<T>::pack(v[0], v[1]);
-        *reinterpret_cast<uint32_t*>(Pp + j1 * AM_PP + c) = Pack2<T>::pack(v[2], v[3]);
-      } else {
-        const int c = (n - 4) * 8 + gc;
+        float h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = Op<T>::to_f(Op<T>::from_f(v[i]));
+        *reinterpret_cast<uint32_t*>(Pp + j0 * AM_PP + c) = Pack2<T>::pack(h[0], h[1]);
+        *reinterpret_cast<uint32_t*>(Pp + j1 * AM_PP + c) = Pack2<T>::pack(h[2], h[3]);
+        *reinterpret_cast<uint32_t*>(Pp + (AM_NPOOL + j0) * AM_PP + c) = Pack2<T>::pack(v[0] - h[0], v[1] - h[1]);
+        *reinterpret_cast<uint32_t*>(Pp + (AM_NPOOL + j1) * AM_PP + c) = Pack2<T>::pack(v[2] - h[2], v[3] - h[3]);
+      }
+    }
+  }
+  {
+    // pass B: g (weight rows 32..95) and its pooling
+    float acc[2][8][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[m][n][i] = 0.f;
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const T* xr = Xs + (row0 + m * 16 + gr) * AM_XP + kt * 16 + gc;
+        a[m][0] = *reinterpret_cast<const uint32_t*>(xr);
+        a[m][1] = *reinterpret_cast<const uint32_t*>(xr + 8 * AM_XP);
+        a[m][2] = *reinterpret_cast<const uint32_t*>(xr + 8);
+        a[m][3] = *reinterpret_cast<const uint32_t*>(xr + 8 * AM_XP + 8);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const T* wr = Wq + (32 + n * 8 + gr) * AM_XP + kt * 16 + gc;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+        mma16816<T>(acc[0][n], a[0], b0, b1);
+        mma16816<T>(acc[1][n], a[1], b0, b1);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float b0 = bq[32 + n * 8 + gc], b1 = bq[32 + n * 8 + gc + 1];
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = fmaxf(acc[0][n][i], acc[1][n][i]) + ((i & 1) ? b1 : b0);      // max(a + b, c + b) = max(a, c) + b
+        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 4));
+      }
+      if ((gr & 1) == 0) {
+        const int j0 = warp * 8 + (gr >> 1), j1 = j0 + 4;
+        const int c = n * 8 + gc;
         Gt[c * AM_OP + j0] = Op<T>::from_f(v[0]);
         Gt[(c + 1) * AM_OP + j0] = Op<T>::from_f(v[1]);
         Gt[c * AM_OP + j1] = Op<T>::from_f(v[2]);
         Gt[(c + 1) * AM_OP + j1] = Op<T>::from_f(v[3]);
       }
     }
-  }
-  // theta as the A operand of the score GEMM (k = 16 channels = accumulator tiles n 0, 1)
-  uint32_t th_a[2][4];
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    th_a[m][0] = Pack2<T>::pack(acc[m][0][0], acc[m][0][1]);
-    th_a[m][1] = Pack2<T>::pack(acc[m][0][2], acc[m][0][3]);
-    th_a[m][2] = Pack2<T>::pack(acc[m][1][0], acc[m][1][1]);
-    th_a[m][3] = Pack2<T>::pack(acc[m][1][2], acc[m][1][3]);
   }
   __syncthreads();
 
@@ -196,11 +252,14 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
   for (int n = 0; n < 8; ++n) {
     const T* pr_ = Pp + (n * 8 + gr) * AM_PP + gc;
     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pr_), b1 = *reinterpret_cast<const uint32_t*>(pr_ + 8);
+    const uint32_t l0 = *reinterpret_cast<const uint32_t*>(pr_ + AM_NPOOL * AM_PP), l1 = *reinterpret_cast<const uint32_t*>(pr_ + AM_NPOOL * AM_PP + 8);
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) s[m][n][i] = 0.f;
-      mma16816<T>(s[m][n], th_a[m], b0, b1);
+      mma16816<T>(s[m][n], th_lo[m], b0, b1);             // small terms first
+      mma16816<T>(s[m][n], th_hi[m], l0, l1);
+      mma16816<T>(s[m][n], th_hi[m], b0, b1);
     }
   }
   uint32_t pa[2][4][4];                                  // P as A operand: [m][k16 tile over keys][4]

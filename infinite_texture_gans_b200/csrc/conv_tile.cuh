@@ -26,8 +26,8 @@ constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;      // input neighbourh
 constexpr int HALO_PX = HALO_W * HALO_H;                     // 180
 constexpr int PLANE_BYTES = HALO_PX * 16;                    // one 8-channel plane of the halo tile: 2880 B
 constexpr int TILE_THREADS = 416;          // warps 0,2,12: producers; 1,3: MMA issuers; 4..11: two epilogue groups
-constexpr int TILE_HDR_BYTES = 1024;       // barriers + per-channel epilogue vectors
-constexpr int TILE_MAX_STAGES = 8;
+constexpr int TILE_HDR_BYTES = 1280;       // barriers + per-channel epilogue vectors
+constexpr int TILE_MAX_STAGES = 12;
 constexpr int TILE_PWARPS = 3;              // producer warps 0, 2, 3: each loads every third tile on its own
 
 struct TileParams {
@@ -43,7 +43,7 @@ struct TileParams {
   int taps_w;              // taps in the weight tensor: 9 | 1 | 16
   int w_bytes;             // bytes of the shared-memory weight image
   int stage_bytes;         // bytes of one input stage (kg planes)
-  int stages, ahead;       // input ring depth; tiles a producer WARP keeps in flight before publishing (1 or 2)
+  int stages, ahead;       // input ring depth; tiles a producer WARP keeps in flight before publishing (0..2)
   int nbuf;                // TMEM accumulator buffers (2 or 4)
   uint32_t tmem_cols;
   uint32_t idesc;
@@ -52,8 +52,6 @@ struct TileParams {
   EpiParams ep;
 };
 
-// timeline trace of CTA 0, tiles 40..47: trace[(it - 40) * 16 + slot] = clock
-#define ITG_TRACE(itv, slot) do { if (p.dbg && blockIdx.x == 0 && (itv) >= 40 && (itv) < 48) p.dbg[4096 + ((itv) - 40) * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
 #define ITG_ACC(slot, tvar) do { if (p.dbg) { const long long now_ = clock64(); dbg_acc[slot] += (unsigned long long)(now_ - tvar); tvar = now_; } } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -120,12 +118,12 @@ conv_tile_kernel(const TileParams p) {
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t bar_full = sbase;                    // [stages]
-  const uint32_t bar_empty = sbase + 64;              // [stages]
-  const uint32_t bar_tfull = sbase + 128;             // [nbuf <= 4] accumulator buffer complete
-  const uint32_t bar_tempty = sbase + 160;            // [nbuf <= 4] accumulator buffer drained
-  const uint32_t tmem_slot = sbase + 192;
-  float* vec = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + 256);   // bias | scale | shift, 64 floats each
+  const uint32_t bar_full = sbase;                    // [stages <= 12]
+  const uint32_t bar_empty = sbase + 128;             // [stages <= 12]
+  const uint32_t bar_tfull = sbase + 256;             // [nbuf <= 4] accumulator buffer complete
+  const uint32_t bar_tempty = sbase + 288;            // [nbuf <= 4] accumulator buffer drained
+  const uint32_t tmem_slot = sbase + 320;
+  float* vec = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + 384);   // bias | scale | shift, 64 floats each
   const uint32_t w_smem = sbase + TILE_HDR_BYTES;
   const uint32_t a_smem = w_smem + (uint32_t)p.w_bytes;
 
@@ -167,6 +165,9 @@ conv_tile_kernel(const TileParams p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Loop bookkeeping without integer division: ring positions advance by a fixed step, tile coordinates by a
+  // precomputed (dy, dx) with carry.  mbarrier waits are done by lane 0 only (a 32-lane try_wait on one barrier
+  // measured ~300 cycles even when already complete) followed by __syncwarp.
   if (warp == 0 || warp == 2 || warp == 12) {                                  // ---- producers ----
     const int pw = warp == 0 ? 0 : (warp == 2 ? 1 : 2);            // producer warp 0..2 loads tiles it = 3k + pw, all 32 lanes on one tile
     const int kg_log2 = 31 - __clz(p.kg);
@@ -177,15 +178,21 @@ conv_tile_kernel(const TileParams p) {
     const bool cg_ok = (p.in_cg_off + j) < cg_total;
     const uint32_t ch_off = (uint32_t)((p.in_cg_off + j) * 8);
     const uint32_t plane_off = (uint32_t)(j * PLANE_BYTES);
+    // per-lane offsets of its halo pixels (<= 45 at kg = 2 ... 12 at kg = 8): computed on the fly, two multiplies each
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
+    const int step = TILE_PWARPS * (int)gridDim.x;
+    const int sdy = step / p.tiles_x, sdx = step - sdy * p.tiles_x;
+    int tile = blockIdx.x + pw * (int)gridDim.x;
+    int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    int s = pw % p.stages;                 // stage of tile it
+    uint32_t ph = (uint32_t)(pw / p.stages) & 1u;
+    int s_pub = s;                         // stage of the tile to publish (ahead iterations behind)
     int k = 0;
-    for (int it = pw; blockIdx.x + it * (int)gridDim.x < p.ntiles; it += TILE_PWARPS, ++k) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int s = it % p.stages;
-      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-      const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;   // halo origin in buffer pixels
-      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+    for (; tile < p.ntiles; tile += step, ++k) {
+      const int y0 = ty * TILE_H, x0 = tx * TILE_W;                            // halo origin in buffer pixels
+      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      __syncwarp();
       ITG_ACC(0, tl);
       const uint32_t dst0 = a_smem + (uint32_t)(s * p.stage_bytes) + plane_off;
       const T* src0 = in + ((size_t)y0 * p.in_pitch + x0) * (size_t)p.in_c + ch_off;
@@ -209,13 +216,19 @@ conv_tile_kernel(const TileParams p) {
         cp_async_wait_dyn(p.ahead);
         ITG_ACC(2, tl);
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((it - p.ahead * TILE_PWARPS) % p.stages));
+        mbar_arrive(bar_full + 8 * s_pub);
+        s_pub += TILE_PWARPS; if (s_pub >= p.stages) s_pub -= p.stages;
         ITG_ACC(3, tl);
       }
+      s += TILE_PWARPS; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+      tx += sdx; ty += sdy; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
     }
     cp_async_wait_dyn(0);
     fence_proxy_async();
-    for (int q = (k > p.ahead ? k - p.ahead : 0); q < k; ++q) mbar_arrive(bar_full + 8 * ((q * TILE_PWARPS + pw) % p.stages));
+    for (int q = (k > p.ahead ? k - p.ahead : 0); q < k; ++q) {
+      mbar_arrive(bar_full + 8 * s_pub);
+      s_pub += TILE_PWARPS; if (s_pub >= p.stages) s_pub -= p.stages;
+    }
     if (p.dbg && pw == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_acc[i];
   } else if (warp == 1 || warp == 3) {                                         // ---- two MMA warps (uniform; one lane issues), alternate tiles ----
     const int mw = warp >> 1;
@@ -223,36 +236,33 @@ conv_tile_kernel(const TileParams p) {
     long long tl = p.dbg ? clock64() : 0;
     const int ksteps = p.kg >> 1;
     const uint32_t w16 = w_smem >> 4, n16 = (uint32_t)p.n;                     // weight image: 16 B per (k-group, n)
+    const int nbuf_log2 = p.nbuf == 4 ? 2 : 1;
+    int s = mw % p.stages;
+    uint32_t ph = (uint32_t)(mw / p.stages) & 1u;
     int it = mw;
     for (int tile = blockIdx.x + mw * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
-      const int s = it % p.stages;
-      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       const int b = it & (p.nbuf - 1);
-      const uint32_t bph = (uint32_t)(it / p.nbuf) & 1u;
-      if (lane == 0) ITG_TRACE(it, 0);
-      mbar_wait(bar_tempty + 8 * b, bph ^ 1u);                                 // epilogue has drained this accumulator
-      if (lane == 0) ITG_TRACE(it, 1);
-      if (p.dbg && it >= p.nbuf && clock64() - tl > 200) {                    // really blocked: how old is the arrival that released us?
-        dbg_acc[3] += (unsigned long long)(clock64() - reinterpret_cast<volatile long long*>(vec + 192)[4 + b]);
+      const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
+      if (lane == 0) {
+        mbar_wait(bar_tempty + 8 * b, bph ^ 1u);                               // epilogue has drained this accumulator
+        ITG_ACC(0, tl);
+        mbar_wait(bar_full + 8 * s, ph);                                       // the halo tile has landed
       }
-      ITG_ACC(0, tl);
-      mbar_wait(bar_full + 8 * s, ph);
-      if (lane == 0) ITG_TRACE(it, 2);
+      __syncwarp();
       ITG_ACC(1, tl);
       tc_fence_after();
       const uint32_t a16 = (a_smem + (uint32_t)(s * p.stage_bytes)) >> 4;
-      if (elect_one_sync()) {                                                        // one lane issues the whole tile, straight-line
+      if (elect_one_sync()) {                                                   // one lane issues the whole tile, straight-line
         const uint32_t d0 = tmem_base + (uint32_t)(b * NPHASE * p.n);
         if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
         else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
         else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
         umma_commit(bar_empty + 8 * s);                                        // input stage may be refilled
         umma_commit(bar_tfull + 8 * b);                                        // accumulators of this tile complete
-        if (p.dbg) reinterpret_cast<volatile long long*>(vec + 192)[b] = clock64();
       }
       __syncwarp();
-      if (lane == 0) ITG_TRACE(it, 3);
       ITG_ACC(2, tl);
+      s += 2; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
     }
     if (p.dbg && lane == 0 && mw == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i];
   } else if (warp >= 4 && warp < 12) {                                         // ---- epilogue ----
@@ -260,16 +270,20 @@ conv_tile_kernel(const TileParams p) {
     const int g = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    EpiParams ep = p.ep;
-    if (ep.bias != nullptr) ep.bias = vec;
-    if (ep.scale != nullptr) { ep.scale = vec + 64; ep.shift = vec + 128; }
+    const EpiParams& ep = p.ep;
+    const uint32_t vec_smem = sbase + 384;              // bias | scale | shift copies (see load_vec8)
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
+    const int nbuf_log2 = p.nbuf == 4 ? 2 : 1;
+    const int step = 2 * (int)gridDim.x;
+    const int sdy = step / p.tiles_x, sdx = step - sdy * p.tiles_x;
+    int tile = blockIdx.x + g * (int)gridDim.x;
+    int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     int it = g;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
+    for (; tile < p.ntiles; tile += step, it += 2) {
       const int b = it & (p.nbuf - 1);
-      const uint32_t bph = (uint32_t)(it / p.nbuf) & 1u;
-      const int y = (tile / p.tiles_x) * TILE_H + (row >> 3), x = (tile % p.tiles_x) * TILE_W + (row & 7);
+      const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
+      const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
       const bool valid = (y < p.m_h) && (x < p.m_w);
       // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier
       uint4 pre[8];
@@ -280,10 +294,8 @@ conv_tile_kernel(const TileParams p) {
         for (int i = 0; i < 8; ++i)
           if (i * 8 < p.n && i * 8 < ep.out_c) pre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
       }
-      if (lane == 0) ITG_TRACE(it, 4 + ew * 3);
-      mbar_wait(bar_tfull + 8 * b, bph);
-      if (lane == 0) ITG_TRACE(it, 5 + ew * 3);
-      if (p.dbg) dbg_acc[2] += (unsigned long long)(clock64() - reinterpret_cast<volatile long long*>(vec + 192)[b]);
+      if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);
+      __syncwarp();
       ITG_ACC(0, tl);
       tc_fence_after();
 #pragma unroll
@@ -291,29 +303,29 @@ conv_tile_kernel(const TileParams p) {
         int oy = y, ox = x;
         if (MODE == ITG_UPCONV) { oy = 2 * y + (q >> 1); ox = 2 * x + (q & 1); }
         const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * NPHASE + q) * p.n);
-        for (int c0 = 0; c0 < p.n; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + (uint32_t)c0, v);
-          if (valid) {
-            float a[8], c[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] = v[i]; c[i] = v[8 + i]; }
-            epilogue8<T, F>(ep, oy, ox, c0, a, PRE ? &pre[(c0 >> 3) & 7] : nullptr);
-            epilogue8<T, F>(ep, oy, ox, c0 + 8, c, PRE ? &pre[((c0 >> 3) + 1) & 7] : nullptr);
+        for (int cc = 0; cc < 4; ++cc) {                                       // n <= 64: compile-time indices keep pre[] in registers
+          const int c0 = cc * 16;
+          if (c0 < p.n) {
+            float v[16];
+            tmem_ld16(trow + (uint32_t)c0, v);
+            if (valid) {
+              float a[8], c[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { a[i] = v[i]; c[i] = v[8 + i]; }
+              epilogue8<T, F>(ep, oy, ox, c0, a, PRE ? &pre[2 * cc] : nullptr, vec_smem);
+              epilogue8<T, F>(ep, oy, ox, c0 + 8, c, PRE ? &pre[2 * cc + 1] : nullptr, vec_smem);
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (p.dbg && ew == 3 && lane == 0) reinterpret_cast<volatile long long*>(vec + 192)[4 + b] = clock64();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-      if (lane == 0) ITG_TRACE(it, 6 + ew * 3);
       ITG_ACC(1, tl);
+      tx += sdx; ty += sdy; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
     }
-    if (p.dbg && ew == 0 && lane == 0) {
-      for (int i = 0; i < 2; ++i) p.dbg[blockIdx.x * 16 + 8 + g * 2 + i] = dbg_acc[i];
-      p.dbg[blockIdx.x * 16 + 12 + g] = dbg_acc[2];
-    }
+    if (p.dbg && ew == 0 && lane == 0) for (int i = 0; i < 2; ++i) p.dbg[blockIdx.x * 16 + 8 + g * 2 + i] = dbg_acc[i];
   }
 
   tc_fence_before();

@@ -242,7 +242,9 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   int stages = (TILE_SMEM_BUDGET - itg::TILE_HDR_BYTES - 128 - p.w_bytes) / p.stage_bytes;
   if (stages > itg::TILE_MAX_STAGES) stages = itg::TILE_MAX_STAGES;
   p.stages = stages;
-  p.ahead = stages >= 7 ? 2 : 1;          // per producer warp; 3 warps x (ahead + 1) tiles in flight must fit the ring
+  p.ahead = (stages - 2) / 3 - 1;         // per producer warp: 3 warps x (ahead + 1) tiles in flight leave two free stages
+  if (p.ahead < 0) p.ahead = 0;
+  if (p.ahead > 2) p.ahead = 2;
   const int nphase = d.mode == ITG_UPCONV ? 4 : 1;
   p.nbuf = (4 * nphase * p.n <= 512) ? 4 : 2;
   uint32_t cols = 32;
@@ -306,23 +308,12 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
     static unsigned long long host[4096 + 128];
     ITG_CUDA(cudaStreamSynchronize(st));
     ITG_CUDA(cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost));
-    const char* names[14] = {"prod.wait_empty", "prod.issue", "prod.wait_group", "prod.fence+arrive", "mma.wait_tempty", "mma.wait_full",
-                             "mma.issue", "mma.arrive2wake", "epi0.wait_tfull", "epi0.work", "epi1.wait_tfull", "epi1.work", "epi0.commit2wake", "epi1.commit2wake"};
+    const char* names[12] = {"prod.wait_empty", "prod.issue", "prod.wait_group", "prod.fence+arrive", "mma.wait_tempty", "mma.wait_full",
+                             "mma.issue", "-", "epi0.wait_tfull", "epi0.work", "epi1.wait_tfull", "epi1.work"};
     fprintf(stderr, "[itg tile dbg] mode=%d k_pad=%d n=%d tiles=%d grid=%d stages=%d flags=%d | kcycles of CTA 0:", d.mode, d.k_pad, d.n_pad,
             p.ntiles, grid, stages, flags);
-    for (int i = 0; i < 14; ++i) if (names[i][0] != '-') fprintf(stderr, " %s=%.1f", names[i], host[i] / 1e3);
+    for (int i = 0; i < 12; ++i) if (names[i][0] != '-') fprintf(stderr, " %s=%.1f", names[i], host[i] / 1e3);
     fprintf(stderr, "\n");
-    if (p.ntiles > 48 * grid) {
-      const unsigned long long t0 = host[4096];
-      for (int i = 0; i < 8; ++i) {
-        fprintf(stderr, "   it=%d mma[wait_tempty %lld got %lld full %lld issued %lld]", 40 + i, (long long)(host[4096 + i * 16] - t0),
-                (long long)(host[4096 + i * 16 + 1] - t0), (long long)(host[4096 + i * 16 + 2] - t0), (long long)(host[4096 + i * 16 + 3] - t0));
-        for (int w = 0; w < 4; ++w)
-          fprintf(stderr, " w%d[%lld %lld %lld]", w, (long long)(host[4096 + i * 16 + 4 + w * 3] - t0), (long long)(host[4096 + i * 16 + 5 + w * 3] - t0),
-                  (long long)(host[4096 + i * 16 + 6 + w * 3] - t0));
-        fprintf(stderr, "\n");
-      }
-    }
   }
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;
@@ -383,7 +374,8 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
   p.w_o = w_o; p.b_o = b_o; p.gamma = gamma; p.out_raw = out_raw; p.out_act = out_act; p.scale = scale; p.shift = shift;
   p.leak = leak; p.border = border;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype != ITG_F32 && patch == itg::AM_PATCH && C <= itg::AM_KMAX) {      // tensor-core kernel (attention_mma.cuh)
+  static const bool legacy_att = getenv("ITG_ATT_CUDA_CORE") != nullptr;       // developer switch: force the fp32 CUDA-core kernel
+  if (!legacy_att && dtype != ITG_F32 && patch == itg::AM_PATCH && C <= itg::AM_KMAX) {      // tensor-core kernel (attention_mma.cuh)
     itg::AttnMmaParams q;
     q.x = x; q.th = th; q.tw = tw; q.C = C; q.xc = xc;
     q.w_theta = w_theta; q.b_theta = b_theta; q.w_phi = w_phi; q.b_phi = b_phi; q.w_g = w_g; q.b_g = b_g;

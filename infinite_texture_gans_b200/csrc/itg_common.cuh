@@ -126,15 +126,33 @@ __device__ __forceinline__ float tanh_fast(float x) {     // MUFU.TANH, abs erro
 enum : int { EF_RES = 1, EF_RAW = 2, EF_ACT = 4, EF_IMG = 8, EF_GENERIC = 1 << 20 };
 
 // Epilogue for 8 consecutive GEMM columns [n, n+8) of output pixel (oy, ox).  acc = raw fp32 accumulators.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// per-channel vector v[n .. n+8): from global memory, or (vec_smem != 0) from the CTA's shared-memory copy at
+// vec_smem + slot * 256 bytes (slot 0 bias, 1 scale, 2 shift; 64 floats each)
+__device__ __forceinline__ void load_vec8(const float* g, uint32_t vec_smem, int slot, int n, float4& a, float4& b) {
+  if (vec_smem != 0) {
+    a = lds_f4(vec_smem + (uint32_t)(slot * 256 + n * 4));
+    b = lds_f4(vec_smem + (uint32_t)(slot * 256 + n * 4 + 16));
+  } else {
+    a = *reinterpret_cast<const float4*>(g + n);
+    b = *reinterpret_cast<const float4*>(g + n + 4);
+  }
+}
+
 // `pre`: the residual's 8 channels already fetched by the caller (16-bit operand types only), or nullptr.
+// `vec_smem`: shared-memory address of the bias | scale | shift copy (tile kernel), 0 = read them from global memory.
 template <typename T, int F = EF_GENERIC>
 __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, int n, float (&acc)[8],
-                                          const uint4* pre = nullptr) {
+                                          const uint4* pre = nullptr, uint32_t vec_smem = 0) {
   constexpr bool G = (F & EF_GENERIC) != 0;
   float v[8];
   if (ep.bias != nullptr) {
-    const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + n);
-    const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + n + 4);
+    float4 b0, b1;
+    load_vec8(ep.bias, vec_smem, 0, n, b0, b1);
     v[0] = acc[0] + b0.x; v[1] = acc[1] + b0.y; v[2] = acc[2] + b0.z; v[3] = acc[3] + b0.w;
     v[4] = acc[4] + b1.x; v[5] = acc[5] + b1.y; v[6] = acc[6] + b1.z; v[7] = acc[7] + b1.w;
   } else {
@@ -225,8 +243,9 @@ __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, i
   if (G ? (ep.out_act != nullptr) : ((F & EF_ACT) != 0)) {
     float a[8];
     if (ep.scale != nullptr) {                       // scale and shift always come as a pair (BN eval fold)
-      const float4 s0 = *reinterpret_cast<const float4*>(ep.scale + n), s1 = *reinterpret_cast<const float4*>(ep.scale + n + 4);
-      const float4 t0 = *reinterpret_cast<const float4*>(ep.shift + n), t1 = *reinterpret_cast<const float4*>(ep.shift + n + 4);
+      float4 s0, s1, t0, t1;
+      load_vec8(ep.scale, vec_smem, 1, n, s0, s1);
+      load_vec8(ep.shift, vec_smem, 2, n, t0, t1);
       a[0] = fmaf(s0.x, v[0], t0.x); a[1] = fmaf(s0.y, v[1], t0.y); a[2] = fmaf(s0.z, v[2], t0.z); a[3] = fmaf(s0.w, v[3], t0.w);
       a[4] = fmaf(s1.x, v[4], t1.x); a[5] = fmaf(s1.y, v[5], t1.y); a[6] = fmaf(s1.z, v[6], t1.z); a[7] = fmaf(s1.w, v[7], t1.w);
     } else {
