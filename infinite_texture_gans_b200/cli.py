@@ -1,0 +1,77 @@
+"""`test_sample.py` of the reference (test_sample.py:11-79) on the B200 path: same flags, same checkpoint format
+({'args': Namespace, 'netG_state_dict': ...}, optional 'module.' prefixes), same output convention (img*0.5+0.5 saved
+next to the checkpoint).  Extra flags default to the reference behaviour."""
+from __future__ import annotations
+
+import argparse
+import os
+from collections import OrderedDict
+
+import torch
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser()
+    # the reference's flags (test_sample.py:14-18)
+    p.add_argument("--output_resolution_height", type=int, default=384, help="output_resolution_height")
+    p.add_argument("--output_resolution_width", type=int, default=384, help="output_resolution_width")
+    p.add_argument("--output_name", type=str, default="241_generated.jpg", help="name of the generated image")
+    p.add_argument("--model_path", type=str, default="results/241_lp_bn_outerpadRepl/300__ema.pth", help="path of the generator network")
+    p.add_argument("--tiles", default=False, action="store_true", help="use tiling of the input (non-local path: not implemented)")
+    # additions
+    p.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"], help="operand precision of the CUDA path")
+    p.add_argument("--schedule", default="oneshot", choices=["oneshot", "sequential"],
+                   help="oneshot: whole patch grid in one device-resident pass; sequential: the shipped 3x3 sub-image schedule")
+    p.add_argument("--seed", type=int, default=None, help="torch.manual_seed before drawing z (the reference has no seed flag)")
+    return p
+
+
+def load_G(state_dict_G, netG):
+    """test_sample.py:32-41: strip 'module.' (nn.DataParallel checkpoints), load, eval."""
+    new_sd = OrderedDict()
+    for k, v in state_dict_G.items():
+        new_sd[k.replace("module.", "") if "module" in k else k] = v
+    netG.load_state_dict(new_sd)
+    netG.eval()
+    return netG
+
+
+def main(argv=None) -> str:
+    from . import generators, utils
+    a = build_parser().parse_args(argv)
+    if not torch.cuda.is_available():
+        raise SystemExit("infinite_texture_gans_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    device = torch.device("cuda:0")
+    folder, _ = os.path.split(a.model_path)
+    torch.serialization.add_safe_globals([argparse.Namespace])          # checkpoints pickle the training Namespace (train.py:207)
+    ckpt = torch.load(a.model_path, map_location="cpu", weights_only=False)
+    args, sd = ckpt["args"], ckpt["netG_state_dict"]
+    if getattr(args, "padding_mode", "local") != "local":
+        raise SystemExit("only --padding_mode local checkpoints are supported (SURVEY 8f: the 'zeros' generator is out of scope)")
+    netG = generators.ResidualPatchGenerator(
+        z_dim=args.z_dim, G_ch=args.G_ch, base_res=args.base_res, n_layers_G=args.n_layers_G, attention=args.attention,
+        img_ch=args.img_ch, leak=args.leak_G, SN=False, type_norm=args.type_norm_G, map_dim=1, padding_mode=args.padding_mode,
+        outer_padding=args.outer_padding, num_patches_h=3, num_patches_w=3, padding_size=1, conv_reduction=2,
+        precision=a.precision)
+    netG = load_G(sd, netG).to(device)
+    print(args)
+    if a.seed is not None:
+        torch.manual_seed(a.seed)
+    with torch.no_grad():
+        img = utils.sample_from_gen_PatchByPatch_test(
+            netG, z_dim=args.z_dim, num_images=1, output_resolution_height=a.output_resolution_height,
+            output_resolution_width=a.output_resolution_width, device=device, schedule=a.schedule).cpu()
+    path = os.path.join(folder, a.output_name)
+    print("The image is saved as:", path)
+    try:
+        from torchvision.utils import save_image
+        save_image(img * 0.5 + 0.5, path)
+    except ImportError:                                                 # torchvision is optional: fall back to PIL
+        from PIL import Image
+        arr = (img[0] * 0.5 + 0.5).clamp(0, 1).mul(255).add(0.5).to(torch.uint8).permute(1, 2, 0).numpy()
+        Image.fromarray(arr).save(path)
+    return path
+
+
+if __name__ == "__main__":
+    main()

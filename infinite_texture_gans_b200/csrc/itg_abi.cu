@@ -47,6 +47,16 @@ EncodeTiledFn get_encode() {
 }
 
 
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 // tile width for an M-grid of width w: as wide as possible (coalesced rows) but no wider than the grid
 int pick_tw_log2(int w) {
   int l = 5;                       // 32 x 4
@@ -131,9 +141,27 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   p.tiles_x = (d.in_w + tw - 1) / tw;
   const int tiles_y = (d.in_h + th - 1) / th;
   p.n_pad = d.n_pad;
-  const int nblocks = (d.n_pad + 255) / 256;
-  if (d.n_pad % (16 * nblocks)) return fail(ITG_ERR_INVALID, "conv: n_pad %d must be a multiple of %d", d.n_pad, 16 * nblocks);
-  p.n_blk = d.n_pad / nblocks;
+  // N blocking: small grids (the 4x4 / 8x8 levels of a 7x21-patch texture have 19 / 74 M-tiles) are split along N
+  // until the launch covers most of the SMs; every CTA then streams fewer weight bytes.  n_blk need not divide n_pad:
+  // the last block computes (and its epilogue drops) columns past n_pad.
+  const int phases = d.mode == ITG_UPCONV ? 4 : 1;
+  const int m_ctas = p.tiles_x * tiles_y * phases;
+  int n_blk = d.n_pad > 256 ? ((d.n_pad + 1) / 2 + 15) / 16 * 16 : d.n_pad;
+  if (n_blk > 256) n_blk = 256;
+  {
+    const int sms = sm_count();
+    const int cand[] = {208, 128, 112, 96, 64, 48, 32};
+    for (int c : cand) {
+      if (c >= n_blk) continue;
+      const int cur = m_ctas * ((d.n_pad + n_blk - 1) / n_blk);
+      if (cur * 10 >= sms * 8) break;                         // already >= 80 % of one wave
+      const int next = m_ctas * ((d.n_pad + c - 1) / c);
+      if (next > sms + sms / 8) break;                         // do not spill into a thin second wave
+      n_blk = c;
+    }
+  }
+  const int nblocks = (d.n_pad + n_blk - 1) / n_blk;
+  p.n_blk = n_blk;
   p.kc = d.k_pad >= 64 ? 64 : d.k_pad;
   p.nchunks = d.k_pad / p.kc;
   // the last chunk only issues the K steps that cover real channels
@@ -200,16 +228,6 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   itg::conv_umma_kernel<T><<<grid, itg::UMMA_THREADS, smem, st>>>(tm_a, tm_b, p);
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;
-}
-
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
 }
 
 constexpr int TILE_SMEM_BUDGET = 200 * 1024;

@@ -137,3 +137,16 @@ def test_product_never_imports_the_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "oracle" not in src.replace("the oracle", "").replace("Oracle", ""), f
+
+
+def test_cli_keeps_the_reference_flags():
+    """test_sample.py:14-18 flag names and defaults."""
+    from infinite_texture_gans_b200.cli import build_parser, load_G
+    a = build_parser().parse_args([])
+    assert (a.output_resolution_height, a.output_resolution_width, a.output_name, a.tiles) == (384, 384, "241_generated.jpg", False)
+    assert a.model_path == "results/241_lp_bn_outerpadRepl/300__ema.pth"
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
+    net = itg.ResidualPatchGenerator(**kw)
+    load_G({"module." + k: v for k, v in sd.items()}, net)          # DataParallel checkpoints
+    assert not net.training
+    assert torch.equal(net.state_dict()["start.conv.weight"], sd["start.conv.weight"])
