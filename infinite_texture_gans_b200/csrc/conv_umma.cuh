@@ -23,7 +23,8 @@ struct UmmaParams {
   int in_c_off;
   int mode;
   int tw_log2, tiles_x;
-  int n_pad, n_blk;
+  int n_pad, n_blk, nblocks;
+  int nwork;             // work items = M tiles x phases x N blocks
   int kc, nchunks, ksteps_last;
   int stages;
   int a_bytes, b_bytes;  // per-stage operand bytes (also the TMA transaction size)
@@ -145,10 +146,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int UMMA_THREADS = 256;
+// Persistent CTAs (grid = min(work items, SM count)).  A work item is one 128-pixel tile x n_blk GEMM columns
+// (x one of the 4 phases of the folded up-sampling conv); a CTA walks its items with the operand ring never draining
+// between items, and with two TMEM accumulator buffers so that the epilogue of item i (two groups of four warps,
+// alternating items) overlaps the TMA loads and MMAs of item i+1.
+constexpr int UMMA_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..7 / 8..11 epilogue groups
 constexpr int UMMA_BAR_BYTES = 1024;
+constexpr int UMMA_MAX_STAGES = 8;
 
-template <typename T>
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <typename T, int F>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -157,8 +167,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const uint32_t bar_full = sbase;                 // [stages] x 8 B
   const uint32_t bar_empty = sbase + 128;          // [stages] x 8 B
-  const uint32_t bar_acc = sbase + 256;            // accumulator complete
-  const uint32_t tmem_slot = sbase + 264;
+  const uint32_t bar_tfull = sbase + 256;          // [2] accumulator buffer complete
+  const uint32_t bar_tempty = sbase + 272;         // [2] accumulator buffer drained
+  const uint32_t tmem_slot = sbase + 288;
   const uint32_t stage0 = sbase + UMMA_BAR_BYTES;
   const uint32_t stage_bytes = (uint32_t)(p.a_stride + p.b_stride);
 
@@ -171,7 +182,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);            // one arrival per epilogue warp of the group
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -181,75 +195,107 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int tile = blockIdx.x;
-  const int n0 = blockIdx.y * p.n_blk;
-  const int phase = blockIdx.z;
   const int tw = 1 << p.tw_log2, th = 128 >> p.tw_log2;
-  const int y0 = (tile / p.tiles_x) * th, x0 = (tile % p.tiles_x) * tw;
   const int ntaps = (p.mode == ITG_CONV3X3) ? 9 : (p.mode == ITG_CONV1X1 ? 1 : 4);
+  const int nphase = (p.mode == ITG_UPCONV) ? 4 : 1;
+  const uint32_t buf_cols = p.tmem_cols >> 1;      // TMEM columns per accumulator buffer
+
+  // work item w -> (tile, phase, n block): n blocks of one tile run on neighbouring CTAs and share its A tiles in L2
+  auto decode = [&](int w, int& tile, int& phase, int& n0) {
+    const int nb = w % p.nblocks, rest = w / p.nblocks;
+    n0 = nb * p.n_blk;
+    phase = rest % nphase;
+    tile = rest / nphase;
+  };
 
   if (warp == 0) {
     if (lane == 0) {                                                   // ---- TMA producer ----
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+        int tile, phase, n0;
+        decode(w, tile, phase, n0);
+        const int y0 = (tile / p.tiles_x) * th, x0 = (tile % p.tiles_x) * tw;
+        for (int t = 0; t < ntaps; ++t) {
+          int dy, dx, wt;
+          tap_offsets(p.mode, phase, t, dy, dx, wt);
+          for (int c = 0; c < p.nchunks; ++c) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(p.a_bytes + p.b_bytes));
+            const uint32_t sa = stage0 + s * stage_bytes;
+            tma_load_3d(sa, &tm_a, bar_full + 8 * s, p.in_c_off + c * p.kc, x0 + dx + 1, y0 + dy + 1);
+            tma_load_2d(sa + p.a_stride, &tm_b, bar_full + 8 * s, c * p.kc, wt * p.n_pad + n0);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {                                              // ---- MMA warp: uniform control flow, one elected lane issues ----
+    int s = 0, li = 0;
+    uint32_t ph = 0;
+    for (int w = blockIdx.x; w < p.nwork; w += gridDim.x, ++li) {
+      const int b = li & 1;
+      const uint32_t bph = (uint32_t)(li >> 1) & 1u;
+      if (lane == 0) mbar_wait(bar_tempty + 8 * b, bph ^ 1u);          // the epilogue has drained this accumulator buffer
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t dcol = tmem_base + (uint32_t)b * buf_cols;
       int it = 0;
       for (int t = 0; t < ntaps; ++t) {
-        int dy, dx, wt;
-        tap_offsets(p.mode, phase, t, dy, dx, wt);
         for (int c = 0; c < p.nchunks; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(p.a_bytes + p.b_bytes));
+          if (lane == 0) mbar_wait(bar_full + 8 * s, ph);
+          __syncwarp();
+          tc_fence_after();
           const uint32_t sa = stage0 + s * stage_bytes;
-          tma_load_3d(sa, &tm_a, bar_full + 8 * s, p.in_c_off + c * p.kc, x0 + dx + 1, y0 + dy + 1);
-          tma_load_2d(sa + p.a_stride, &tm_b, bar_full + 8 * s, c * p.kc, wt * p.n_pad + n0);
+          const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
+          const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
+          const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
+          if (elect_one_sync()) {                 // +32 B (16 channels) per K step inside the swizzle row
+            umma_f16(dcol, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u);
+            if (nk > 1) umma_f16(dcol, adesc + 2, bdesc + 2, p.idesc, 1u);
+            if (nk > 2) umma_f16(dcol, adesc + 4, bdesc + 4, p.idesc, 1u);
+            if (nk > 3) umma_f16(dcol, adesc + 6, bdesc + 6, p.idesc, 1u);
+            umma_commit(bar_empty + 8 * s);       // frees the stage when these MMAs have read it
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
+      if (elect_one_sync()) umma_commit(bar_tfull + 8 * b);            // accumulators of this item complete
+      __syncwarp();
     }
-    __syncwarp();
-  } else if (warp == 1) {                                                  // ---- MMA warp: uniform control flow, one elected lane issues ----
-    int it = 0;
-    for (int t = 0; t < ntaps; ++t) {
-      for (int c = 0; c < p.nchunks; ++c, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t sa = stage0 + s * stage_bytes;
-        const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
-        const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
-        const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
-        if (elect_one_sync()) {                 // +32 B (16 channels) per K step inside the swizzle row
-          umma_f16(tmem_base, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u);
-          if (nk > 1) umma_f16(tmem_base, adesc + 2, bdesc + 2, p.idesc, 1u);
-          if (nk > 2) umma_f16(tmem_base, adesc + 4, bdesc + 4, p.idesc, 1u);
-          if (nk > 3) umma_f16(tmem_base, adesc + 6, bdesc + 6, p.idesc, 1u);
-          umma_commit(bar_empty + 8 * s);       // frees the stage when these MMAs have read it
-        }
-        __syncwarp();
-      }
-    }
-    if (elect_one_sync()) umma_commit(bar_acc);  // accumulator complete
-    __syncwarp();
-  } else if (warp >= 4) {                                                // ---- epilogue ----
+  } else if (warp >= 4) {                                              // ---- epilogue: group g drains every second item ----
+    const int g = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    const int y = y0 + (row >> p.tw_log2), x = x0 + (row & (tw - 1));
-    const bool valid = (y < p.m_h) && (x < p.m_w);
-    int oy = y, ox = x;
-    if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
-    for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
-      float v[16];
-      tmem_ld16(trow + (uint32_t)c0, v);
-      if (valid) {
-        float a[8], b[8];
+    int li = g;
+    for (int w = blockIdx.x + g * gridDim.x; w < p.nwork; w += 2 * gridDim.x, li += 2) {
+      int tile, phase, n0;
+      decode(w, tile, phase, n0);
+      const uint32_t bph = (uint32_t)(li >> 1) & 1u;
+      const int y = (tile / p.tiles_x) * th + (row >> p.tw_log2), x = (tile % p.tiles_x) * tw + (row & (tw - 1));
+      const bool valid = (y < p.m_h) && (x < p.m_w);
+      int oy = y, ox = x;
+      if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
+      if (lane == 0) mbar_wait(bar_tfull + 8 * g, bph);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)g * buf_cols;
+      for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
+        if (valid) {
+          float a[8], b[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
-        epilogue8<T>(p.ep, oy, ox, n0 + c0, a);
-        epilogue8<T>(p.ep, oy, ox, n0 + c0 + 8, b);
+          for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+          epilogue8<T, F>(p.ep, oy, ox, n0 + c0, a);
+          epilogue8<T, F>(p.ep, oy, ox, n0 + c0 + 8, b);
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(bar_tempty + 8 * g);
     }
   }
 

@@ -162,6 +162,8 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   }
   const int nblocks = (d.n_pad + n_blk - 1) / n_blk;
   p.n_blk = n_blk;
+  p.nblocks = nblocks;
+  p.nwork = m_ctas * nblocks;
   p.kc = d.k_pad >= 64 ? 64 : d.k_pad;
   p.nchunks = d.k_pad / p.kc;
   // the last chunk only issues the K steps that cover real channels
@@ -180,12 +182,12 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   const int total_iters = ntaps * p.nchunks;
   const int stage_bytes = p.a_stride + p.b_stride;
   int stages = (200 * 1024) / stage_bytes;
-  if (stages > 4) stages = 4;
+  if (stages > itg::UMMA_MAX_STAGES) stages = itg::UMMA_MAX_STAGES;
   if (stages > total_iters) stages = total_iters;
   if (stages < 1) return fail(ITG_ERR_UNSUPPORTED, "conv: stage of %d bytes does not fit shared memory", stage_bytes);
   p.stages = stages;
   uint32_t cols = 32;
-  while ((int)cols < p.n_blk) cols <<= 1;
+  while ((int)cols < 2 * p.n_blk) cols <<= 1;              // two accumulator buffers
   p.tmem_cols = cols;
   const uint32_t fmt = (d.dtype == ITG_BF16) ? 1u : 0u;    // kind::f16 operand format
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_blk >> 3) << 17) | ((128u >> 4) << 24);
@@ -218,14 +220,34 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   }
 
   const int smem = itg::UMMA_BAR_BYTES + stages * stage_bytes + 1024;
-  static int smem_set_h = 0, smem_set_b = 0;
-  int& smem_set = (d.dtype == ITG_BF16) ? smem_set_b : smem_set_h;
-  if (smem > smem_set) {
-    ITG_CUDA(cudaFuncSetAttribute(itg::conv_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
+  const int grid = p.nwork < sm_count() ? p.nwork : sm_count();
+  int flags = itg::EF_GENERIC;
+  if (!d.mod_x && !d.out_f32 && d.res_kind != ITG_RES_F32) {
+    if (d.out_img) flags = itg::EF_IMG;
+    else flags = (d.res_kind == ITG_RES_GRID ? itg::EF_RES : 0) | (d.out_raw ? itg::EF_RAW : 0) | (d.out_act ? itg::EF_ACT : 0);
   }
-  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)nblocks, d.mode == ITG_UPCONV ? 4u : 1u);
-  itg::conv_umma_kernel<T><<<grid, itg::UMMA_THREADS, smem, st>>>(tm_a, tm_b, p);
+#define ITG_UMMA_LAUNCH(FL)                                                                                            \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      ITG_CUDA(cudaFuncSetAttribute(itg::conv_umma_kernel<T, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    itg::conv_umma_kernel<T, FL><<<grid, itg::UMMA_THREADS, smem, st>>>(tm_a, tm_b, p);                                \
+  } while (0)
+  {
+    constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
+    switch (flags) {
+      case A: ITG_UMMA_LAUNCH(A); break;
+      case R: ITG_UMMA_LAUNCH(R); break;
+      case A | S: ITG_UMMA_LAUNCH(A | S); break;
+      case R | A: ITG_UMMA_LAUNCH(R | A); break;
+      case R | S: ITG_UMMA_LAUNCH(R | S); break;
+      case R | A | S: ITG_UMMA_LAUNCH(R | A | S); break;
+      default: ITG_UMMA_LAUNCH(G); break;
+    }
+  }
+#undef ITG_UMMA_LAUNCH
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;
 }
