@@ -239,9 +239,13 @@ def main():
     out_pin = torch.empty((1, cfg.img_ch, th * P, tw * P), dtype=torch.float32).pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
+    band_graph = None
+
     def step_device():
         if use_graph:
             eng.replay(th, tw, L.IMG_MERGED)
+        elif band_graph is not None:
+            band_graph.replay()
         else:
             plan.run(hooks)
 
@@ -271,7 +275,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b_) for a, b_ in evs)
-    launches = (plan.n_launches * args.steps) if use_graph else (eng.backend.launches - launches0)
+    launches = (plan.n_launches * args.steps) if (use_graph or band_graph is not None) else (eng.backend.launches - launches0)
     clk = clocks.stop()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -347,7 +351,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": desc + (f"; x{world} row bands, one per GPU, per-layer halo exchange (NCCL send/recv)" if world > 1 else ""),
                            "weights": "random init (reference init scheme)", "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
-                           "launch": "CUDA graph replay" if use_graph else "eager launches", "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
+                           "launch": "CUDA graph replay" if (use_graph or band_graph is not None) else "eager launches", "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": roof}

@@ -25,7 +25,8 @@ constexpr int TILE_W = 8, TILE_H = 16;                       // output tile = 12
 constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;      // input neighbourhood
 constexpr int HALO_PX = HALO_W * HALO_H;                     // 180
 constexpr int PLANE_BYTES = HALO_PX * 16;                    // one 8-channel plane of the halo tile: 2880 B
-constexpr int TILE_THREADS = 416;          // warps 0,2,12: producers; 1,3: MMA issuers; 4..11: two epilogue groups
+constexpr int TILE_EPI_GROUPS = 2;          // epilogue groups of four warps; group g drains tiles it = g (mod 4)
+constexpr int TILE_THREADS = 32 * (4 + 4 * TILE_EPI_GROUPS + 1);   // warps 0,2,last: producers; 1,3: MMA issuers; 4..4+4G-1: epilogue
 constexpr int TILE_HDR_BYTES = 1280;       // barriers + per-channel epilogue vectors
 constexpr int TILE_MAX_STAGES = 12;
 constexpr int TILE_PWARPS = 3;              // producer warps 0, 2, 3: each loads every third tile on its own
@@ -90,9 +91,30 @@ template <> struct TileMode<ITG_CONV3X3> { static constexpr int NPHASE = 1, NTAP
 template <> struct TileMode<ITG_CONV1X1> { static constexpr int NPHASE = 1, NTAPS = 1; };
 template <> struct TileMode<ITG_UPCONV> { static constexpr int NPHASE = 4, NTAPS = 4; };
 
+// tcgen05.mma executed by the lane whose `leader` flag is set, WITHOUT a branch: the surrounding code stays in uniform
+// control flow, so the descriptors are computed on the uniform datapath instead of being moved lane -> uniform
+// register (R2UR + ELECT loops) for every instruction.
+__device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(leader)
+      : "memory");
+}
+
 // All MMAs of one tile: NPHASE accumulators x NTAPS taps x KSTEPS 16-channel steps, fully unrolled.
 template <int MODE, int KSTEPS>
-__device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w16, uint32_t n16, uint32_t kg, uint32_t idesc) {
+__device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w16, uint32_t n16, uint32_t kg, uint32_t idesc, uint32_t leader) {
 #pragma unroll
   for (int q = 0; q < TileMode<MODE>::NPHASE; ++q) {
 #pragma unroll
@@ -104,7 +126,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w
       for (int ks = 0; ks < KSTEPS; ++ks) {
         const uint64_t adesc = desc_noswz(a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16) + shift16, PLANE_BYTES / 16, HALO_W);
         const uint64_t bdesc = desc_noswz(w16 + ((uint32_t)wt * kg + (uint32_t)(2 * ks)) * n16, n16, 8);
-        umma_f16(d0 + (uint32_t)q * n16, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+        umma_f16_pred(d0 + (uint32_t)q * n16, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u, leader);
       }
     }
   }
@@ -168,7 +190,7 @@ conv_tile_kernel(const TileParams p) {
   // Loop bookkeeping without integer division: ring positions advance by a fixed step, tile coordinates by a
   // precomputed (dy, dx) with carry.  mbarrier waits are done by lane 0 only (a 32-lane try_wait on one barrier
   // measured ~300 cycles even when already complete) followed by __syncwarp.
-  if (warp == 0 || warp == 2 || warp == 12) {                                  // ---- producers ----
+  if (warp == 0 || warp == 2 || warp == 4 + 4 * TILE_EPI_GROUPS) {                // ---- producers ----
     const int pw = warp == 0 ? 0 : (warp == 2 ? 1 : 2);            // producer warp 0..2 loads tiles it = 3k + pw, all 32 lanes on one tile
     const int kg_log2 = 31 - __clz(p.kg);
     const int cg_total = p.in_c >> 3;
@@ -252,21 +274,22 @@ conv_tile_kernel(const TileParams p) {
       ITG_ACC(1, tl);
       tc_fence_after();
       const uint32_t a16 = (a_smem + (uint32_t)(s * p.stage_bytes)) >> 4;
-      if (elect_one_sync()) {                                                   // one lane issues the whole tile, straight-line
+      {                                                                          // one lane issues the whole tile, predicated, no branch
+        const uint32_t leader = elect_one_sync() ? 1u : 0u;
         const uint32_t d0 = tmem_base + (uint32_t)(b * NPHASE * p.n);
-        if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
-        else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
-        else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
-        umma_commit(bar_empty + 8 * s);                                        // input stage may be refilled
-        umma_commit(bar_tfull + 8 * b);                                        // accumulators of this tile complete
+        if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc, leader);
+        else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc, leader);
+        else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc, leader);
+        umma_commit_pred(bar_empty + 8 * s, leader);                           // input stage may be refilled
+        umma_commit_pred(bar_tfull + 8 * b, leader);                           // accumulators of this tile complete
       }
       __syncwarp();
       ITG_ACC(2, tl);
       s += 2; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
     }
     if (p.dbg && lane == 0 && mw == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i];
-  } else if (warp >= 4 && warp < 12) {                                         // ---- epilogue ----
-    // two groups of four warps; group g drains every second tile of this CTA (accumulator buffer it % nbuf)
+  } else if (warp >= 4 && warp < 4 + 4 * TILE_EPI_GROUPS) {                    // ---- epilogue ----
+    // groups of four warps; group g drains every TILE_EPI_GROUPS-th tile of this CTA (accumulator buffer it % nbuf)
     const int g = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
@@ -275,12 +298,14 @@ conv_tile_kernel(const TileParams p) {
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
     const int nbuf_log2 = p.nbuf == 4 ? 2 : 1;
-    const int step = 2 * (int)gridDim.x;
+    // a group may wait at most one barrier phase ahead (parity waits), so no more groups than accumulator buffers
+    const int ngroups = p.nbuf < TILE_EPI_GROUPS ? p.nbuf : TILE_EPI_GROUPS;
+    const int step = ngroups * (int)gridDim.x;
     const int sdy = step / p.tiles_x, sdx = step - sdy * p.tiles_x;
-    int tile = blockIdx.x + g * (int)gridDim.x;
+    int tile = g < ngroups ? blockIdx.x + g * (int)gridDim.x : p.ntiles;
     int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     int it = g;
-    for (; tile < p.ntiles; tile += step, it += 2) {
+    for (; tile < p.ntiles; tile += step, it += ngroups) {
       const int b = it & (p.nbuf - 1);
       const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
       const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);

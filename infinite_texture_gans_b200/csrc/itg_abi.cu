@@ -286,7 +286,7 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   if (p.ahead < 0) p.ahead = 0;
   if (p.ahead > 2) p.ahead = 2;
   const int nphase = d.mode == ITG_UPCONV ? 4 : 1;
-  p.nbuf = (4 * nphase * p.n <= 512) ? 4 : 2;
+  p.nbuf = (4 * nphase * p.n <= 512) ? 4 : 2;   // with 2 buffers, epilogue groups 2, 3 share buffers 0, 1 (still correct: tiles alternate)
   uint32_t cols = 32;
   while ((int)cols < p.nbuf * nphase * p.n) cols <<= 1;
   p.tmem_cols = cols;
