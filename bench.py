@@ -327,11 +327,17 @@ def main():
                                          + px * (px // 4) * (c // 2))
         conv_alg_flops = total_flops - att_flops
         achieved = conv_alg_flops / (conv_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_umma_kernel (all conv launches of one step)" if args.precision != "fp32"
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(f"{args.workload}:{args.precision}")
+        roof = {"bound": "tensor", "kernel": "conv_umma_kernel + conv_tile_kernel (all conv launches of one step)" if args.precision != "fp32"
                 else "conv_direct_kernel", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
-                "frac": achieved / bf16_peak, "peak_kind": f"{peak_kind} bf16 burst", "traffic": None,
+                "frac": achieved / bf16_peak, "peak_kind": f"{peak_kind} bf16 burst", "traffic": traffic,
+                "traffic_note": "DRAM bytes of all conv launches of one step (ncu, profiles/r01_summary.md); compulsory z in + fp32 image out = "
+                                f"{(cfg.z_dim * (th * 4 + 2) * (tw * 4 + 2) + cfg.img_ch * th * tw * P * P) * 4} B",
                 "conv_ms_per_step": conv_ms, "all_launches_ms_per_step": all_ms,
-                "step_tflops": total_flops / (ms_per_step / 1e3) / 1e12 / world * world,
+                "step_tflops": total_flops * world / (ms_per_step / 1e3) / 1e12,
                 "step_frac_of_peak": total_flops * world / (ms_per_step / 1e3) / 1e12 / (bf16_peak * world)}
         if args.profile_out:
             rows = []

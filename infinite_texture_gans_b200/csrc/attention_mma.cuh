@@ -82,21 +82,11 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
   const int NT_OUT = (xc + 7) >> 3;                      // n8 tiles of the output (storage channels)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gr = lane >> 2, gc = (lane & 3) * 2;         // fragment row / column-pair of this lane
-  const int pid = blockIdx.x;
-  const int pr = pid / p.tw, pc = pid % p.tw;
   const int H = p.th * AM_PATCH, W = p.tw * AM_PATCH;
   const T* xg = reinterpret_cast<const T*>(p.x);
 
-  // ---------------- stage x, weights and biases ----------------
+  // ---------------- stage weights and biases once per CTA (CTAs are persistent over patches) ----------------
   {
-    const int groups = KT * 2;                           // 8-channel groups per row incl. zero padding
-    for (int i = threadIdx.x; i < AM_NPX * groups; i += 256) {
-      const int px = i / groups, g8 = i % groups;
-      const int y = pr * AM_PATCH + (px >> 4), x = pc * AM_PATCH + (px & 15);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (g8 * 8 < xc) v = *reinterpret_cast<const uint4*>(xg + grid_off(y, x, W, xc, g8 * 8));
-      *reinterpret_cast<uint4*>(Xs + px * AM_XP + g8 * 8) = v;
-    }
     const int kpad = KT * 16;
     for (int i = threadIdx.x; i < AM_QKV * kpad; i += 256) {
       const int n = i / kpad, k = i % kpad;
@@ -123,9 +113,24 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
     }
     for (int i = threadIdx.x; i < AM_KMAX; i += 256) bo[i] = i < C ? p.b_o[i] : 0.f;
   }
-  __syncthreads();
 
   const int row0 = warp * 32;                            // this warp's first pixel
+  for (int pid = blockIdx.x; pid < p.th * p.tw; pid += gridDim.x) {
+  const int pr = pid / p.tw, pc = pid % p.tw;
+  __syncthreads();                                       // weights staged / previous patch fully streamed out
+  // ---------------- stage the x tile of this patch ----------------
+  {
+    const int groups = KT * 2;                           // 8-channel groups per row incl. zero padding
+    for (int i = threadIdx.x; i < AM_NPX * groups; i += 256) {
+      const int px = i / groups, g8 = i % groups;
+      const int y = pr * AM_PATCH + (px >> 4), x = pc * AM_PATCH + (px & 15);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (g8 * 8 < xc) v = *reinterpret_cast<const uint4*>(xg + grid_off(y, x, W, xc, g8 * 8));
+      *reinterpret_cast<uint4*>(Xs + px * AM_XP + g8 * 8) = v;
+    }
+  }
+  __syncthreads();
+
   // ---------------- 1. [theta | phi | g] = X Wqkv^T, 2. 2x2 max pooling ----------------
   // Pooling: m = 0 / 1 are the patch rows 2w / 2w+1 (same px); fragment rows gr, gr^1 are px pairs -> one shuffle
   // across lanes ^4; lanes with even gr then own window jx = gr/2 (c0,c1) and jx + 4 (c2,c3) of window row jy = w.
@@ -370,6 +375,7 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
       }
     }
   }
+  }  // patch loop
 }
 
 }  // namespace itg

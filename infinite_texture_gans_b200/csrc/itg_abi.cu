@@ -424,10 +424,10 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
     static bool attr_h = false, attr_b = false;
     if (dtype == ITG_F16) {
       if (!attr_h) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_h = true; }
-      itg::attention_mma_kernel<__half><<<th * tw, 256, itg::AM_SMEM, st>>>(q);
+      itg::attention_mma_kernel<__half><<<(th * tw < sm_count() ? th * tw : sm_count()), 256, itg::AM_SMEM, st>>>(q);
     } else {
       if (!attr_b) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_b = true; }
-      itg::attention_mma_kernel<__nv_bfloat16><<<th * tw, 256, itg::AM_SMEM, st>>>(q);
+      itg::attention_mma_kernel<__nv_bfloat16><<<(th * tw < sm_count() ? th * tw : sm_count()), 256, itg::AM_SMEM, st>>>(q);
     }
     ITG_CUDA(cudaGetLastError());
     return ITG_OK;
