@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo rows over peer-mapped memory (NVLink P2P) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
     args = ap.parse_args()
@@ -201,7 +202,7 @@ def main():
     import infinite_texture_gans_b200 as itg
     from infinite_texture_gans_b200 import _lib as L
     from infinite_texture_gans_b200.config import GenConfig, flops_per_patch
-    from infinite_texture_gans_b200.halo import BandHalo
+    from infinite_texture_gans_b200.halo import BandHalo, P2PBandHalo
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,7 +231,21 @@ def main():
     if maps_full is not None:
         maps_band = [m[:, :, r0 * b * 2 ** i:(r0 + th) * b * 2 ** i + 4].contiguous() for i, m in enumerate(maps_full)]
     plan = eng.plan(th, tw, L.IMG_MERGED)
-    band = BandHalo() if world > 1 else None
+    band, p2p = None, False
+    if world > 1:
+        if args.halo == "p2p":
+            try:
+                band, p2p = P2PBandHalo(plan), True
+            except Exception as e:                                   # noqa: BLE001  (IPC unavailable: fall back to NCCL send/recv)
+                print(f"[bench] rank {rank}: P2P halo setup failed ({type(e).__name__}: {e}); using NCCL send/recv", file=sys.stderr)
+            ok = torch.tensor([1 if p2p else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if p2p:
+                    band.close()
+                band, p2p = None, False
+        if band is None:
+            band = BandHalo()
     hooks = band.hooks(plan) if band is not None else None
     use_graph = (not args.no_graph) and world == 1
 
@@ -241,13 +256,18 @@ def main():
 
     band_graph = None
 
+    def step_eager():
+        if p2p:
+            band.begin_step()
+        plan.run(hooks)
+
     def step_device():
         if use_graph:
             eng.replay(th, tw, L.IMG_MERGED)
         elif band_graph is not None:
             band_graph.replay()
         else:
-            plan.run(hooks)
+            step_eager()
 
     def barrier():
         if dist is not None:
@@ -259,6 +279,14 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
+    if p2p and not args.no_graph:
+        # launches + device-side halo exchanges of one step in ONE CUDA graph (no NCCL inside, nothing to deadlock on)
+        band_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(band_graph):
+            step_eager()
+        for _ in range(3):
+            step_device()
+        barrier()
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = eng.backend.launches
@@ -275,7 +303,8 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b_) for a, b_ in evs)
-    launches = (plan.n_launches * args.steps) if (use_graph or band_graph is not None) else (eng.backend.launches - launches0)
+    per_step = plan.n_launches + ((len(plan.halo_points) + 1) if p2p else 0)      # + device-side halo exchanges + step counter
+    launches = (per_step * args.steps) if (use_graph or band_graph is not None) else (eng.backend.launches - launches0)
     clk = clocks.stop()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -293,7 +322,8 @@ def main():
                 noise=(z_pin, maps_pin), return_on_device=True, graph=use_graph)
         else:
             plan.set_inputs(z_pin[0], None if maps_pin is None else [m[0, 0] for m in maps_pin])
-            img = plan.run(hooks)
+            step_device()
+            img = plan.out
         out_pin.copy_(img, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -355,7 +385,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": desc + (f"; x{world} row bands, one per GPU, per-layer halo exchange (NCCL send/recv)" if world > 1 else ""),
+                "config": {"workload": desc + (f"; x{world} row bands, one per GPU, per-layer halo rows over " + ("NVLink P2P (itg_halo_exchange)" if p2p else "NCCL send/recv") if world > 1 else ""),
                            "weights": "random init (reference init scheme)", "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
                            "launch": "CUDA graph replay" if (use_graph or band_graph is not None) else "eager launches", "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
                 "clocks": clk, "gpu_launches": launches,
@@ -364,6 +394,9 @@ def main():
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
+    if p2p:
+        barrier()
+        band.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -167,6 +167,26 @@ int itg_copy_rect(int32_t dtype, const void* src, int32_t src_pitch, int32_t sy,
                   void* dst, int32_t dst_pitch, int32_t dy, int32_t dx, int32_t h, int32_t w, int32_t c,
                   void* stream);
 
+/* Row-band multi-GPU split: halo rows of one conv2d_lp input over peer-mapped memory (NVLink P2P), one launch, no host
+ * involvement.  Pushes this rank's first / last interior pixel row into the up / down neighbour's inbox row and
+ * publishes *step in the neighbour's flag; waits for the neighbours' flags to reach *step and copies the local inbox
+ * rows into the top / bottom frame row of `grid`.  NULL inbox = no neighbour on that side.  `up_*` / `down_*` are
+ * pointers into the NEIGHBOURS' memory (CUDA IPC mappings), `top_*` / `bot_*` are local.  Replaces the `.cpu()` / `.to(device)`
+ * halo hand-off of LocalPadder.update_padding_variables (layers.py:117-139) for the multi-GPU case. */
+int itg_halo_exchange(int32_t dtype, void* grid, int32_t h, int32_t w, int32_t c, void* up_inbox, void* down_inbox,
+                      int32_t* up_flag, int32_t* down_flag, const void* top_inbox, const void* bot_inbox,
+                      int32_t* top_flag, int32_t* bot_flag, const int32_t* step, void* stream);
+/* Advance the device-resident step counter that itg_halo_exchange publishes / waits for (once per Generator pass). */
+int itg_step_advance(int32_t* step, void* stream);
+
+/* Exchange buffers for itg_halo_exchange: device memory of THIS process that neighbour ranks map through CUDA IPC
+ * (one process per GPU).  alloc zero-fills `bytes` on `device` and returns the pointer plus a 64-byte handle to send to
+ * the neighbours; open maps a neighbour's handle into this process (peer access is enabled lazily by the runtime). */
+int itg_ipc_alloc(int32_t device, uint64_t bytes, void** ptr, void* handle64);
+int itg_ipc_open(int32_t device, const void* handle64, void** ptr);
+int itg_ipc_close(void* ptr);
+int itg_ipc_free(void* ptr);
+
 /* Fill the frame of a grid tensor from its interior (replicate) or with zeros (constant): F.pad of
  * layers.py:82.  sides: bit0 top, bit1 bottom, bit2 left, bit3 right. */
 int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int32_t border, int32_t sides,

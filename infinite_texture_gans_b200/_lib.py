@@ -27,7 +27,8 @@ DTYPE_OF = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 TORCH_OF = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 
 EXPORTS = ("itg_version", "itg_last_error", "itg_conv_desc_size", "itg_conv_fwd", "itg_attention_fwd",
-           "itg_pack_nchw", "itg_pack_map_taps", "itg_copy_rect", "itg_fill_frame")
+           "itg_pack_nchw", "itg_pack_map_taps", "itg_copy_rect", "itg_fill_frame", "itg_halo_exchange", "itg_step_advance",
+           "itg_ipc_alloc", "itg_ipc_open", "itg_ipc_close", "itg_ipc_free")
 
 
 class ConvDesc(C.Structure):
@@ -79,6 +80,18 @@ def load() -> C.CDLL:
     lib.itg_pack_map_taps.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.itg_copy_rect.restype = C.c_int
     lib.itg_copy_rect.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]
+    lib.itg_halo_exchange.restype = C.c_int
+    lib.itg_halo_exchange.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 10
+    lib.itg_step_advance.restype = C.c_int
+    lib.itg_step_advance.argtypes = [C.c_void_p, C.c_void_p]
+    lib.itg_ipc_alloc.restype = C.c_int
+    lib.itg_ipc_alloc.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.itg_ipc_open.restype = C.c_int
+    lib.itg_ipc_open.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.itg_ipc_close.restype = C.c_int
+    lib.itg_ipc_close.argtypes = [C.c_void_p]
+    lib.itg_ipc_free.restype = C.c_int
+    lib.itg_ipc_free.argtypes = [C.c_void_p]
     lib.itg_fill_frame.restype = C.c_int
     lib.itg_fill_frame.argtypes = [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]
     if lib.itg_conv_desc_size() != C.sizeof(ConvDesc):

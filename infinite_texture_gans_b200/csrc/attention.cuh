@@ -222,6 +222,75 @@ __global__ void copy_rect_kernel(const T* __restrict__ src, int src_pitch, int s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// row-band multi-GPU halo exchange over peer-mapped memory (NVLink P2P), no host involvement
+// ------------------------------------------------------------------------------------------------
+// One launch per conv2d_lp input: blocks 0 / 1 PUSH this rank's first / last interior pixel row (frame columns
+// included) into the up / down neighbour's inbox and then publish the step number in the neighbour's flag
+// (system-scope release); blocks 2 / 3 wait (bounded spin, system-scope acquire) for the up / down neighbour's flag to
+// reach the step number and PULL the inbox row into this rank's top / bottom frame row.  Inboxes and flags are one per
+// halo point, so a neighbour can never overwrite a row that has not been consumed.
+struct HaloXchgParams {
+  void* grid;            // (h+2) x (w+2) x c framed grid tensor of this rank
+  int h, w, c;
+  void* up_inbox;        // peer pointers (NULL at the first / last band): neighbour's bottom / top inbox row
+  void* down_inbox;
+  int* up_flag;          // peer pointers: neighbour's "bottom arrived" / "top arrived" flags
+  int* down_flag;
+  const void* top_inbox; // local inbox rows written by the neighbours
+  const void* bot_inbox;
+  int* top_flag;         // local flags
+  int* bot_flag;
+  const int* step;       // device-resident step counter (advanced once per Generator pass)
+};
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) halo_xchg_kernel(const HaloXchgParams p) {
+  const int role = blockIdx.x;                       // 0 push up, 1 push down, 2 pull top, 3 pull bottom
+  const size_t row_elems = (size_t)(p.w + 2) * p.c;
+  const size_t chunks = row_elems / 8;               // 16-byte chunks (c is a multiple of 8)
+  T* g = reinterpret_cast<T*>(p.grid);
+  const int step = *p.step;
+  if (role < 2) {
+    T* dst = reinterpret_cast<T*>(role == 0 ? p.up_inbox : p.down_inbox);
+    int* flag = role == 0 ? p.up_flag : p.down_flag;
+    if (dst == nullptr) return;
+    const T* src = g + (size_t)(role == 0 ? 1 : p.h) * row_elems;
+    for (size_t i = threadIdx.x; i < chunks; i += blockDim.x)
+      reinterpret_cast<Vec8<T>*>(dst)[i] = reinterpret_cast<const Vec8<T>*>(src)[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(flag, step);
+  } else {
+    const T* src = reinterpret_cast<const T*>(role == 2 ? p.top_inbox : p.bot_inbox);
+    int* flag = role == 2 ? p.top_flag : p.bot_flag;
+    if (src == nullptr) return;
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(flag) < step) {
+        if (clock64() - t0 > 8000000000LL) {         // ~4 s: a neighbour died; fail the launch instead of hanging the GPU
+          printf("itg: halo exchange timed out waiting for step %d (flag %d)\n", step, ld_acquire_sys(flag));
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+    __threadfence_system();
+    T* dst = g + (size_t)(role == 2 ? 0 : p.h + 1) * row_elems;
+    for (size_t i = threadIdx.x; i < chunks; i += blockDim.x)
+      reinterpret_cast<Vec8<T>*>(dst)[i] = reinterpret_cast<const Vec8<T>*>(src)[i];
+  }
+}
+
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
 // F.pad(x, (1,1,1,1), mode) on the frame of a grid tensor; sides: bit0 top, bit1 bottom, bit2 left, bit3 right
 template <typename T>
 __global__ void fill_frame_kernel(T* __restrict__ t, int h, int w, int c, int border, int sides) {

@@ -489,6 +489,60 @@ int itg_copy_rect(int32_t dtype, const void* src, int32_t src_pitch, int32_t sy,
   return ITG_OK;
 }
 
+// ---- peer-mapped exchange buffers for the row-band split (CUDA IPC; one process per GPU) ----
+int itg_ipc_alloc(int32_t device, uint64_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail(ITG_ERR_INVALID, "ipc_alloc: bad arguments");
+  ITG_CUDA(cudaSetDevice(device));
+  ITG_CUDA(cudaMalloc(ptr, bytes));
+  ITG_CUDA(cudaMemset(*ptr, 0, bytes));
+  ITG_CUDA(cudaDeviceSynchronize());
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  ITG_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), *ptr));
+  return ITG_OK;
+}
+int itg_ipc_open(int32_t device, const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(ITG_ERR_INVALID, "ipc_open: bad arguments");
+  ITG_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  ITG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ITG_OK;
+}
+int itg_ipc_close(void* ptr) {
+  if (ptr) ITG_CUDA(cudaIpcCloseMemHandle(ptr));
+  return ITG_OK;
+}
+int itg_ipc_free(void* ptr) {
+  if (ptr) ITG_CUDA(cudaFree(ptr));
+  return ITG_OK;
+}
+
+int itg_halo_exchange(int32_t dtype, void* grid, int32_t h, int32_t w, int32_t c, void* up_inbox, void* down_inbox, int32_t* up_flag,
+                      int32_t* down_flag, const void* top_inbox, const void* bot_inbox, int32_t* top_flag, int32_t* bot_flag,
+                      const int32_t* step, void* stream) {
+  if (!grid || !step || c % 8 || h < 1 || w < 1) return fail(ITG_ERR_INVALID, "halo_exchange: bad arguments");
+  if ((up_inbox && !up_flag) || (down_inbox && !down_flag) || (top_inbox && !top_flag) || (bot_inbox && !bot_flag))
+    return fail(ITG_ERR_INVALID, "halo_exchange: an inbox needs its flag");
+  itg::HaloXchgParams p;
+  p.grid = grid; p.h = h; p.w = w; p.c = c;
+  p.up_inbox = up_inbox; p.down_inbox = down_inbox; p.up_flag = up_flag; p.down_flag = down_flag;
+  p.top_inbox = top_inbox; p.bot_inbox = bot_inbox; p.top_flag = top_flag; p.bot_flag = bot_flag; p.step = step;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == ITG_F32) itg::halo_xchg_kernel<float><<<4, 1024, 0, st>>>(p);
+  else if (dtype == ITG_F16) itg::halo_xchg_kernel<__half><<<4, 1024, 0, st>>>(p);
+  else if (dtype == ITG_BF16) itg::halo_xchg_kernel<__nv_bfloat16><<<4, 1024, 0, st>>>(p);
+  else return fail(ITG_ERR_INVALID, "halo_exchange: bad dtype");
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int itg_step_advance(int32_t* step, void* stream) {
+  if (!step) return fail(ITG_ERR_INVALID, "step_advance: null counter");
+  itg::step_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step);
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
 int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int32_t border, int32_t sides, void* stream) {
   if (!t || c % 8 || h < 1 || w < 1 || (border != ITG_BORDER_REPLICATE && border != ITG_BORDER_CONSTANT))
     return fail(ITG_ERR_INVALID, "fill_frame: bad arguments");

@@ -135,3 +135,84 @@ class BandHalo:
         for r in dist.batch_isend_irecv(ops):
             r.wait()
         self.bytes_sent += buf[1].numel() * buf.element_size() * ((up is not None) + (down is not None))
+
+
+class P2PBandHalo:
+    """Row-band split with the halo rows moved by the GPUs themselves over peer-mapped memory (NVLink P2P):
+    one `itg_halo_exchange` launch per conv2d_lp input pushes this rank's border rows into the neighbours' inboxes,
+    publishes a step number in their flags, waits for the neighbours' flags and pulls the received rows into the
+    frame.  No host synchronisation and no NCCL call inside a step, so a whole step (launches + exchanges) can be
+    captured in one CUDA graph.  torch.distributed is only used once, to swap the CUDA IPC handles."""
+
+    FLAG_BYTES = 4096
+
+    def __init__(self, plan: Plan, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib as L
+        self.lib = L.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.plan = plan
+        dev = plan.out.device
+        self.device_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        es = plan.halo_points[0].grid.buf.element_size()
+        self.dtype_code = L.DTYPE_OF[plan.halo_points[0].grid.buf.dtype]
+        # layout of the exchange buffer: [flags + step counter | per halo point: top inbox row, bottom inbox row]
+        self.offsets = []
+        off = self.FLAG_BYTES
+        for hp in plan.halo_points:
+            row = ((hp.grid.w + 2) * hp.grid.c * es + 255) // 256 * 256
+            self.offsets.append((off, off + row))
+            off += 2 * row
+        self.bytes = off
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        L.check(self.lib.itg_ipc_alloc(self.device_index, self.bytes, C.byref(ptr), handle))
+        self.base = ptr.value
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (self.device_index, handle.raw, self.bytes), group)
+        if any(i[2] != self.bytes for i in infos):
+            raise RuntimeError("row bands must have the same shape on every rank for the P2P exchange")
+        self.peer = {}
+        for nb in (self.rank - 1, self.rank + 1):
+            if 0 <= nb < self.world:
+                p = C.c_void_p()
+                L.check(self.lib.itg_ipc_open(self.device_index, infos[nb][1], C.byref(p)))
+                self.peer[nb] = p.value
+        dist.barrier(group)
+        self.step_ptr = self.base + 8 * len(plan.halo_points) + 64      # int32 step counter after the flags
+        self.bytes_per_step = sum((hp.grid.w + 2) * hp.grid.c * es for hp in plan.halo_points) * len(self.peer)   # pushed by this rank
+
+    def _args(self, k: int, hp: HaloPoint):
+        up, down = self.peer.get(self.rank - 1), self.peer.get(self.rank + 1)
+        top_off, bot_off = self.offsets[k]
+        flag = lambda base, i: base + 4 * i
+        return (self.dtype_code, hp.grid.buf.data_ptr(), hp.grid.h, hp.grid.w, hp.grid.c,
+                (up + bot_off) if up else None, (down + top_off) if down else None,          # my first row -> up neighbour's BOTTOM inbox
+                flag(up, 2 * k + 1) if up else None, flag(down, 2 * k) if down else None,
+                (self.base + top_off) if up else None, (self.base + bot_off) if down else None,
+                flag(self.base, 2 * k) if up else None, flag(self.base, 2 * k + 1) if down else None,
+                self.step_ptr)
+
+    def hooks(self, plan: Plan):
+        from . import _lib as L
+        assert plan is self.plan
+        if self.world == 1:
+            return None
+        hooks = {}
+        for k, hp in enumerate(plan.halo_points):
+            args = self._args(k, hp)
+            hooks[hp.step] = (lambda args=args: L.check(self.lib.itg_halo_exchange(*args, L.stream_ptr())))
+        return hooks
+
+    def begin_step(self) -> None:
+        """Advance the device-resident step counter (first launch of every Generator pass)."""
+        from . import _lib as L
+        L.check(self.lib.itg_step_advance(self.step_ptr, L.stream_ptr()))
+
+    def close(self) -> None:
+        for p in self.peer.values():
+            self.lib.itg_ipc_close(p)
+        self.peer = {}
+        if self.base:
+            self.lib.itg_ipc_free(self.base)
+            self.base = 0
