@@ -111,3 +111,18 @@ def test_no_cpu_fallback():
     net = make_generator(kw, sd, "fp16")          # left on the CPU
     with pytest.raises(itg.ItgError, match="CUDA"):
         itg.utils.generate_full_grid(net, z)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one node")
+def test_two_gpu_band_split_equals_single_gpu():
+    """Row-band split over two GPUs with the device-side P2P halo exchange == single-GPU image, bit for bit
+    (tools/band_check.py under torchrun; also replays the step from a CUDA graph)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "band_check.py"), "p2p"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "max|bands - single GPU| = 0.000e+00" in r.stdout
