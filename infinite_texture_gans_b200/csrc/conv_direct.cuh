@@ -78,6 +78,10 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
   if (!valid) return;
   int oy = y, ox = x;
   if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
+  if (p.ep.mod_x != nullptr) {
+    epilogue_ssm16<T>(p.ep, oy, ox, n0, acc);
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < DIRECT_NB; g += 8) {
     float v[8];

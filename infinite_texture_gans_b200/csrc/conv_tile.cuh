@@ -91,27 +91,6 @@ template <> struct TileMode<ITG_CONV3X3> { static constexpr int NPHASE = 1, NTAP
 template <> struct TileMode<ITG_CONV1X1> { static constexpr int NPHASE = 1, NTAPS = 1; };
 template <> struct TileMode<ITG_UPCONV> { static constexpr int NPHASE = 4, NTAPS = 4; };
 
-// tcgen05.mma executed by the lane whose `leader` flag is set, WITHOUT a branch: the surrounding code stays in uniform
-// control flow, so the descriptors are computed on the uniform datapath instead of being moved lane -> uniform
-// register (R2UR + ELECT loops) for every instruction.
-__device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(leader)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_pred(uint32_t bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar), "r"(leader)
-      : "memory");
-}
-
 // All MMAs of one tile: NPHASE accumulators x NTAPS taps x KSTEPS 16-channel steps, fully unrolled.
 template <int MODE, int KSTEPS>
 __device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w16, uint32_t n16, uint32_t kg, uint32_t idesc, uint32_t leader) {

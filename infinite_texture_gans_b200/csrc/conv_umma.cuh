@@ -121,6 +121,27 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// tcgen05.mma executed by the lane whose `leader` flag is set, WITHOUT a branch: the surrounding code stays in uniform
+// control flow, so the descriptors are computed on the uniform datapath instead of being moved lane -> uniform
+// register (R2UR + ELECT loops) for every instruction.
+__device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(leader)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -251,18 +272,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
           const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
           const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
-          if (elect_one_sync()) {                 // +32 B (16 channels) per K step inside the swizzle row
-            umma_f16(dcol, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u);
-            if (nk > 1) umma_f16(dcol, adesc + 2, bdesc + 2, p.idesc, 1u);
-            if (nk > 2) umma_f16(dcol, adesc + 4, bdesc + 4, p.idesc, 1u);
-            if (nk > 3) umma_f16(dcol, adesc + 6, bdesc + 6, p.idesc, 1u);
-            umma_commit(bar_empty + 8 * s);       // frees the stage when these MMAs have read it
+          {                                       // branch-free: the elected lane's predicate guards each instruction,
+            const uint32_t leader = elect_one_sync() ? 1u : 0u;   // descriptors stay on the uniform datapath
+            umma_f16_pred(dcol, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u, leader);           // +32 B (16 channels) per K step
+            umma_f16_pred(dcol, adesc + 2, bdesc + 2, p.idesc, 1u, (nk > 1) ? leader : 0u);
+            umma_f16_pred(dcol, adesc + 4, bdesc + 4, p.idesc, 1u, (nk > 2) ? leader : 0u);
+            umma_f16_pred(dcol, adesc + 6, bdesc + 6, p.idesc, 1u, (nk > 3) ? leader : 0u);
+            umma_commit_pred(bar_empty + 8 * s, leader);   // frees the stage when these MMAs have read it
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
-      if (elect_one_sync()) umma_commit(bar_tfull + 8 * b);            // accumulators of this item complete
+      umma_commit_pred(bar_tfull + 8 * b, elect_one_sync() ? 1u : 0u);   // accumulators of this item complete
       __syncwarp();
     }
   } else if (warp >= 4) {                                              // ---- epilogue: group g drains every second item ----
@@ -286,11 +308,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
         if (valid) {
-          float a[8], b[8];
+          if ((F & EF_GENERIC) != 0 && p.ep.mod_x != nullptr) {
+            epilogue_ssm16<T>(p.ep, oy, ox, n0 + c0, v);
+          } else {
+            float a[8], b[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
-          epilogue8<T, F>(p.ep, oy, ox, n0 + c0, a);
-          epilogue8<T, F>(p.ep, oy, ox, n0 + c0 + 8, b);
+            for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+            epilogue8<T, F>(p.ep, oy, ox, n0 + c0, a);
+            epilogue8<T, F>(p.ep, oy, ox, n0 + c0 + 8, b);
+          }
         }
       }
       tc_fence_before();

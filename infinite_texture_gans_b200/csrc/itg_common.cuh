@@ -260,6 +260,40 @@ __device__ __forceinline__ void epilogue8(const EpiParams& ep, int oy, int ox, i
   }
 }
 
+// SSM epilogue for 16 consecutive GEMM columns [n, n+16) = 8 channels (gamma_c, beta_c interleaved) of pixel (oy, ox):
+//   y_c = (1 + gamma_c) * (x_c - mean_c) * rstd_c + beta_c   [-> activation], one 16-byte load of x and one 16-byte store.
+// StochasticSpatialModulation.forward, models/layers.py:228-234.
+template <typename T>
+__device__ __forceinline__ void epilogue_ssm16(const EpiParams& ep, int oy, int ox, int n, const float (&acc)[16]) {
+  const int c0 = n >> 1;
+  if (c0 >= ep.out_c) return;
+  float g[16];
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = *reinterpret_cast<const float4*>(ep.bias + n + 4 * q);
+      g[4 * q] = acc[4 * q] + b.x; g[4 * q + 1] = acc[4 * q + 1] + b.y; g[4 * q + 2] = acc[4 * q + 2] + b.z; g[4 * q + 3] = acc[4 * q + 3] + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] = acc[i];
+  }
+  float x[8];
+  load8(reinterpret_cast<const T*>(ep.mod_x) + grid_off(oy >> ep.mod_shift, ox >> ep.mod_shift, ep.mod_w, ep.mod_c, c0), x);
+  const float4 m0 = *reinterpret_cast<const float4*>(ep.mod_mean + c0), m1 = *reinterpret_cast<const float4*>(ep.mod_mean + c0 + 4);
+  const float4 r0 = *reinterpret_cast<const float4*>(ep.mod_rstd + c0), r1 = *reinterpret_cast<const float4*>(ep.mod_rstd + c0 + 4);
+  const float mean[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+  const float rstd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float xh = (x[i] - mean[i]) * rstd[i];
+    const float v = (1.f + g[2 * i]) * xh + g[2 * i + 1];
+    y[i] = ep.act_linear ? v : act_fn(v, ep.leak);
+  }
+  store8_framed(reinterpret_cast<T*>(ep.out_act), oy, ox, ep.out_h, ep.out_w, ep.out_c, c0, y, ep.border);
+}
+
 // tap geometry shared by both conv kernels
 struct TapGeom {
   int ntaps;        // taps per phase
