@@ -253,6 +253,8 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 
 template <typename T>
 __global__ void __launch_bounds__(1024) halo_xchg_kernel(const HaloXchgParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int role = blockIdx.x;                       // 0 push up, 1 push down, 2 pull top, 3 pull bottom
   const size_t row_elems = (size_t)(p.w + 2) * p.c;
   const size_t chunks = row_elems / 8;               // 16-byte chunks (c is a multiple of 8)

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
   const T* xg = reinterpret_cast<const T*>(p.x);
 
   // ---------------- stage weights and biases once per CTA (CTAs are persistent over patches) ----------------
+  pdl_launch_dependents();
   {
     const int kpad = KT * 16;
     for (int i = threadIdx.x; i < AM_QKV * kpad; i += 256) {
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256, 1) attention_mma_kernel(const AttnMmaPara
   }
 
   const int row0 = warp * 32;                            // this warp's first pixel
+  pdl_wait();                                            // x (the previous launch's output) is complete from here on
   for (int pid = blockIdx.x; pid < p.th * p.tw; pid += gridDim.x) {
   const int pr = pid / p.tw, pc = pid % p.tw;
   __syncthreads();                                       // weights staged / previous patch fully streamed out

@@ -128,6 +128,7 @@ conv_tile_kernel(const TileParams p) {
   const uint32_t w_smem = sbase + TILE_HDR_BYTES;
   const uint32_t a_smem = w_smem + (uint32_t)p.w_bytes;
 
+  pdl_launch_dependents();
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(bar_full + 8 * i, 32);
@@ -165,6 +166,7 @@ conv_tile_kernel(const TileParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                          // activations of the previous launch are complete and visible from here on
 
   // Loop bookkeeping without integer division: ring positions advance by a fixed step, tile coordinates by a
   // precomputed (dy, dx) with carry.  mbarrier waits are done by lane 0 only (a 32-lane try_wait on one barrier

@@ -194,6 +194,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t stage0 = sbase + UMMA_BAR_BYTES;
   const uint32_t stage_bytes = (uint32_t)(p.a_stride + p.b_stride);
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -215,6 +216,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                          // the previous launch's outputs (our activations) are complete from here on
 
   const int tw = 1 << p.tw_log2, th = 128 >> p.tw_log2;
   const int ntaps = (p.mode == ITG_CONV3X3) ? 9 : (p.mode == ITG_CONV1X1 ? 1 : 4);

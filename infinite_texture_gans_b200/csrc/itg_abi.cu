@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <cstdlib>
 
 #include "attention.cuh"
@@ -29,6 +30,22 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (expr);                                                                     \
     if (e_ != cudaSuccess) return fail(ITG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
+
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; it calls
+// pdl_wait() (griddepcontrol.wait) before touching activations.  ITG_NO_PDL=1 turns the attribute off.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl = getenv("ITG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -233,7 +250,7 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
       ITG_CUDA(cudaFuncSetAttribute(itg::conv_umma_kernel<T, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    itg::conv_umma_kernel<T, FL><<<grid, itg::UMMA_THREADS, smem, st>>>(tm_a, tm_b, p);                                \
+    ITG_CUDA(launch_pdl(itg::conv_umma_kernel<T, FL>, dim3(grid), dim3(itg::UMMA_THREADS), smem, st, tm_a, tm_b, p));  \
   } while (0)
   {
     constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
@@ -317,7 +334,7 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
       ITG_CUDA(cudaFuncSetAttribute(itg::conv_tile_kernel<T, FL, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    itg::conv_tile_kernel<T, FL, MD><<<grid, itg::TILE_THREADS, smem, st>>>(p);                                       \
+    ITG_CUDA(launch_pdl(itg::conv_tile_kernel<T, FL, MD>, dim3(grid), dim3(itg::TILE_THREADS), smem, st, p));         \
   } while (0)
   constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
   if (d.mode == ITG_CONV3X3) {
@@ -424,10 +441,10 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
     static bool attr_h = false, attr_b = false;
     if (dtype == ITG_F16) {
       if (!attr_h) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_h = true; }
-      itg::attention_mma_kernel<__half><<<(th * tw < sm_count() ? th * tw : sm_count()), 256, itg::AM_SMEM, st>>>(q);
+      ITG_CUDA(launch_pdl(itg::attention_mma_kernel<__half>, dim3(th * tw < sm_count() ? th * tw : sm_count()), dim3(256), itg::AM_SMEM, st, q));
     } else {
       if (!attr_b) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_b = true; }
-      itg::attention_mma_kernel<__nv_bfloat16><<<(th * tw < sm_count() ? th * tw : sm_count()), 256, itg::AM_SMEM, st>>>(q);
+      ITG_CUDA(launch_pdl(itg::attention_mma_kernel<__nv_bfloat16>, dim3(th * tw < sm_count() ? th * tw : sm_count()), dim3(256), itg::AM_SMEM, st, q));
     }
     ITG_CUDA(cudaGetLastError());
     return ITG_OK;
@@ -528,9 +545,9 @@ int itg_halo_exchange(int32_t dtype, void* grid, int32_t h, int32_t w, int32_t c
   p.up_inbox = up_inbox; p.down_inbox = down_inbox; p.up_flag = up_flag; p.down_flag = down_flag;
   p.top_inbox = top_inbox; p.bot_inbox = bot_inbox; p.top_flag = top_flag; p.bot_flag = bot_flag; p.step = step;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == ITG_F32) itg::halo_xchg_kernel<float><<<4, 1024, 0, st>>>(p);
-  else if (dtype == ITG_F16) itg::halo_xchg_kernel<__half><<<4, 1024, 0, st>>>(p);
-  else if (dtype == ITG_BF16) itg::halo_xchg_kernel<__nv_bfloat16><<<4, 1024, 0, st>>>(p);
+  if (dtype == ITG_F32) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<float>, dim3(4), dim3(1024), 0, st, p));
+  else if (dtype == ITG_F16) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<__half>, dim3(4), dim3(1024), 0, st, p));
+  else if (dtype == ITG_BF16) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<__nv_bfloat16>, dim3(4), dim3(1024), 0, st, p));
   else return fail(ITG_ERR_INVALID, "halo_exchange: bad dtype");
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;

@@ -9,6 +9,14 @@
 
 namespace itg {
 
+// Programmatic dependent launch (PDL): kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while their predecessor in the stream is still draining.  pdl_launch_dependents() lets the successor's CTAs
+// be scheduled as soon as SM resources free up; pdl_wait() blocks until the predecessor grid has completed and its
+// memory is visible -- everything a kernel does before pdl_wait() (barrier init, TMEM allocation, parking weights
+// in shared memory) must not touch activations.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------
 // operand types
 // ---------------------------------------------------------------------------------------------------
