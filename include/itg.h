@@ -170,12 +170,14 @@ int itg_copy_rect(int32_t dtype, const void* src, int32_t src_pitch, int32_t sy,
 /* Row-band multi-GPU split: halo rows of one conv2d_lp input over peer-mapped memory (NVLink P2P), one launch, no host
  * involvement.  Pushes this rank's first / last interior pixel row into the up / down neighbour's inbox row and
  * publishes *step in the neighbour's flag; waits for the neighbours' flags to reach *step and copies the local inbox
- * rows into the top / bottom frame row of `grid`.  NULL inbox = no neighbour on that side.  `up_*` / `down_*` are
+ * rows into the top / bottom frame row of `grid`.  NULL inbox = no neighbour on that side.  `roles` selects what this
+ * launch does (bit 0 push up, 1 push down, 2 pull top, 3 pull bottom; 15 = everything) so that the pushes can be
+ * issued right after the producer and the pulls right before the consumer, with independent work in between.  `up_*` / `down_*` are
  * pointers into the NEIGHBOURS' memory (CUDA IPC mappings), `top_*` / `bot_*` are local.  Replaces the `.cpu()` / `.to(device)`
  * halo hand-off of LocalPadder.update_padding_variables (layers.py:117-139) for the multi-GPU case. */
 int itg_halo_exchange(int32_t dtype, void* grid, int32_t h, int32_t w, int32_t c, void* up_inbox, void* down_inbox,
                       int32_t* up_flag, int32_t* down_flag, const void* top_inbox, const void* bot_inbox,
-                      int32_t* top_flag, int32_t* bot_flag, const int32_t* step, void* stream);
+                      int32_t* top_flag, int32_t* bot_flag, const int32_t* step, int32_t roles, void* stream);
 /* Advance the device-resident step counter that itg_halo_exchange publishes / waits for (once per Generator pass). */
 int itg_step_advance(int32_t* step, void* stream);
 

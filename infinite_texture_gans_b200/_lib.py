@@ -81,7 +81,7 @@ def load() -> C.CDLL:
     lib.itg_copy_rect.restype = C.c_int
     lib.itg_copy_rect.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]
     lib.itg_halo_exchange.restype = C.c_int
-    lib.itg_halo_exchange.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 10
+    lib.itg_halo_exchange.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9 + [C.c_int32, C.c_void_p]
     lib.itg_step_advance.restype = C.c_int
     lib.itg_step_advance.argtypes = [C.c_void_p, C.c_void_p]
     lib.itg_ipc_alloc.restype = C.c_int

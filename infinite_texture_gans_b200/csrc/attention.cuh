@@ -242,6 +242,7 @@ struct HaloXchgParams {
   int* top_flag;         // local flags
   int* bot_flag;
   const int* step;       // device-resident step counter (advanced once per Generator pass)
+  int roles;             // bit 0 push up, bit 1 push down, bit 2 pull top, bit 3 pull bottom
 };
 
 __device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(1024) halo_xchg_kernel(const HaloXchgParams p)
   pdl_launch_dependents();
   pdl_wait();
   const int role = blockIdx.x;                       // 0 push up, 1 push down, 2 pull top, 3 pull bottom
+  if (!((p.roles >> role) & 1)) return;
   const size_t row_elems = (size_t)(p.w + 2) * p.c;
   const size_t chunks = row_elems / 8;               // 16-byte chunks (c is a multiple of 8)
   T* g = reinterpret_cast<T*>(p.grid);

@@ -536,14 +536,14 @@ int itg_ipc_free(void* ptr) {
 
 int itg_halo_exchange(int32_t dtype, void* grid, int32_t h, int32_t w, int32_t c, void* up_inbox, void* down_inbox, int32_t* up_flag,
                       int32_t* down_flag, const void* top_inbox, const void* bot_inbox, int32_t* top_flag, int32_t* bot_flag,
-                      const int32_t* step, void* stream) {
-  if (!grid || !step || c % 8 || h < 1 || w < 1) return fail(ITG_ERR_INVALID, "halo_exchange: bad arguments");
+                      const int32_t* step, int32_t roles, void* stream) {
+  if (!grid || !step || c % 8 || h < 1 || w < 1 || roles < 1 || roles > 15) return fail(ITG_ERR_INVALID, "halo_exchange: bad arguments");
   if ((up_inbox && !up_flag) || (down_inbox && !down_flag) || (top_inbox && !top_flag) || (bot_inbox && !bot_flag))
     return fail(ITG_ERR_INVALID, "halo_exchange: an inbox needs its flag");
   itg::HaloXchgParams p;
   p.grid = grid; p.h = h; p.w = w; p.c = c;
   p.up_inbox = up_inbox; p.down_inbox = down_inbox; p.up_flag = up_flag; p.down_flag = down_flag;
-  p.top_inbox = top_inbox; p.bot_inbox = bot_inbox; p.top_flag = top_flag; p.bot_flag = bot_flag; p.step = step;
+  p.top_inbox = top_inbox; p.bot_inbox = bot_inbox; p.top_flag = top_flag; p.bot_flag = bot_flag; p.step = step; p.roles = roles;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == ITG_F32) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<float>, dim3(4), dim3(1024), 0, st, p));
   else if (dtype == ITG_F16) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<__half>, dim3(4), dim3(1024), 0, st, p));

@@ -139,10 +139,11 @@ class _VGrid:
 @dataclass
 class HaloPoint:
     """A conv2d_lp input: grid tensor `grid` feeds conv `name`; `r` = per-patch size at that tensor's resolution."""
-    step: int
+    step: int            # index of the producing step: frame patching / pushes run right after it
     name: str
     grid: Grid
     r: int
+    pull_step: int = -1  # index of the step right before the consumer conv (>= step): pulls may run as late as after it
 
 
 class Plan:
@@ -197,13 +198,20 @@ class Plan:
               leak=None, linear=False, border=None, res=None, res_shift=0, mod=None,
               mod_shift=0, mod_prefix=None, window=None, out_hw=None, out_c=None, img=False):
         self._touch(src, out_raw, out_act, res, mod)
+        self._note_consumer(src)
         self._steps.append(("conv", dict(name=name, mode=mode, src=src, wkey=wkey, k=k, out_raw=out_raw, out_act=out_act,
                                          norm=norm, leak=leak, linear=linear, border=border, res=res,
                                          res_shift=res_shift, mod=mod, mod_shift=mod_shift, mod_prefix=mod_prefix,
                                          window=window, out_hw=out_hw, out_c=out_c, img=img)))
 
     def _halo(self, name: str, g: _VGrid, r: int):
-        self._halo_tmp.append((len(self._steps) - 1, name, g, r))
+        self._halo_tmp.append([len(self._steps) - 1, name, g, r, -1])
+
+    def _note_consumer(self, src: _VGrid):
+        """Called before a conv reading `src` is appended: remember the last step before the consumer of a halo grid."""
+        for h in self._halo_tmp:
+            if h[2] is src and h[4] < 0:
+                h[4] = len(self._steps) - 1
 
     # ------------------------------------------------------------------------------------------
     # network topology
@@ -220,6 +228,7 @@ class Plan:
         else:
             a_last = self._build_ssm(z)
         self._touch(a_last)
+        self._note_consumer(a_last)
         self._steps.append(("conv", dict(name="final", mode=L.CONV3X3, src=a_last, wkey="final.conv.", k=None, out_raw=None,
                                          out_act=None, norm=None, leak=None, linear=False, border=None, res=None,
                                          res_shift=0, mod=None, mod_shift=0, mod_prefix=None, window=None, out_hw=None,
@@ -249,6 +258,12 @@ class Plan:
                 self._conv(p + "conv1", L.CONV3X3, a, p + "conv1.conv.", out_act=a2, norm=p + "bn2.", border=self.border)
                 res, res_shift = h_raw, 0
             else:
+                self._conv(p + "conv1", L.UPCONV, a, p + "conv1.conv.", out_act=a2, norm=p + "bn2.", border=self.border,
+                           out_hw=(H, W))
+            self._halo(p + "conv2", a2, r)
+            if k > 1:
+                # the 1x1 shortcut does not need a2: it sits between conv1 and conv2 so that, in the row-band multi-GPU
+                # split, a2's halo rows travel while it runs
                 if ci != co:
                     s = self._g(f"s.{p}", H // 2, W // 2, c_store(co))
                     self._conv(p + "conv3", L.CONV1X1, h_raw, p + "conv3.", out_raw=s)
@@ -256,9 +271,6 @@ class Plan:
                 else:
                     res = h_raw
                 res_shift = 1
-                self._conv(p + "conv1", L.UPCONV, a, p + "conv1.conv.", out_act=a2, norm=p + "bn2.", border=self.border,
-                           out_hw=(H, W))
-            self._halo(p + "conv2", a2, r)
             att_here = k == 3 and cfg.attention
             next_norm = "bn." if last else f"block{k + 1}.bn1."
             next_name = "final" if last else f"block{k + 1}.conv1"
@@ -367,7 +379,7 @@ class Plan:
             buf = self.arena[o:o + n * es].view(self.dtype).view(v.h + 2, v.w + 2, v.c)
             v.grid = Grid(buf, v.h, v.w, v.c)
         self.grids = {v.name: v.grid for v in self._vgrids}
-        self.halo_points = [HaloPoint(step, name, g.grid, r) for step, name, g, r in self._halo_tmp]
+        self.halo_points = [HaloPoint(step, name, g.grid, r, max(pull, step)) for step, name, g, r, pull in self._halo_tmp]
 
         be, w = self.backend, self.w
         self.ops: List[Tuple[str, object]] = []

@@ -198,11 +198,22 @@ class P2PBandHalo:
         assert plan is self.plan
         if self.world == 1:
             return None
-        hooks = {}
+        lib = self.lib
+        per_step = {}
         for k, hp in enumerate(plan.halo_points):
             args = self._args(k, hp)
-            hooks[hp.step] = (lambda args=args: L.check(self.lib.itg_halo_exchange(*args, L.stream_ptr())))
-        return hooks
+            if hp.pull_step == hp.step:          # consumer follows immediately: one launch pushes and pulls
+                per_step.setdefault(hp.step, []).append((args, 15))
+            else:                                # independent work in between: push now, pull right before the consumer
+                per_step.setdefault(hp.step, []).append((args, 3))
+                per_step.setdefault(hp.pull_step, []).append((args, 12))
+
+        def make(calls):
+            def run():
+                for args, roles in calls:
+                    L.check(lib.itg_halo_exchange(*args, roles, L.stream_ptr()))
+            return run
+        return {step: make(calls) for step, calls in per_step.items()}
 
     def begin_step(self) -> None:
         """Advance the device-resident step counter (first launch of every Generator pass)."""
