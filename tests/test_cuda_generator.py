@@ -126,3 +126,31 @@ def test_two_gpu_band_split_equals_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "max|bands - single GPU| = 0.000e+00" in r.stdout
+
+
+def test_cli_end_to_end(tmp_path):
+    """test_sample.py flow (test_sample.py:11-79): checkpoint {'args': Namespace, 'netG_state_dict'} with DataParallel
+    'module.' prefixes -> image file next to the checkpoint; the saved 8-bit image matches the oracle to 8-bit precision."""
+    import argparse
+    import numpy as np
+    from PIL import Image
+    from infinite_texture_gans_b200 import cli
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
+    args = argparse.Namespace(z_dim=kw["z_dim"], G_ch=kw["G_ch"], base_res=4, n_layers_G=kw["n_layers_G"], attention=kw["attention"],
+                              img_ch=3, leak_G=kw["leak"], type_norm_G=kw["type_norm"], padding_mode="local",
+                              outer_padding=kw["outer_padding"])
+    ckpt = tmp_path / "net.pth"
+    torch.save({"args": args, "netG_state_dict": {"module." + k: v for k, v in sd.items()}}, ckpt)
+    H, W = int(d["H"]), int(d["W"])
+    path = cli.main(["--model_path", str(ckpt), "--output_resolution_height", str(H), "--output_resolution_width", str(W),
+                     "--output_name", "out.png", "--seed", "123", "--precision", "fp32"])
+    img = np.asarray(Image.open(path)).astype(np.float32) / 255.0
+    assert img.shape == (H, W, 3)
+    # same seed -> same noise as the reference draw order; oracle on that noise
+    torch.manual_seed(123)
+    geo = O.geometry(H, W, ocfg)
+    z2 = torch.randn(1, kw["z_dim"], geo["total_h"] * 4 + 2, geo["total_w"] * 4 + 2)
+    with torch.no_grad():
+        ref = O.forward_merged(sd, ocfg, z2)[:, :, :H, :W]
+    ref8 = (ref[0] * 0.5 + 0.5).clamp(0, 1).permute(1, 2, 0).numpy()
+    assert np.abs(img - ref8).max() <= 1.5 / 255.0
