@@ -25,6 +25,10 @@ struct UmmaParams {
   int tw_log2, tiles_x;
   int n_pad, n_blk, nblocks;
   int nwork;             // work items = M tiles x phases x N blocks
+  int cluster;           // CTAs per cluster (1, 2, 4 or 8).  > 1: the cluster's CTAs are the N blocks of one (tile, phase)
+                         // item and share its activation tiles through TMA multicast; nblocks == cluster
+  int nitems;            // M tiles x phases
+  unsigned long long* dbg;  // optional per-role cycle counters of CTA 0 (ITG_TILE_DBG=1)
   int kc, nchunks, ksteps_last;
   int stages;
   int a_bytes, b_bytes;  // per-stage operand bytes (also the TMA transaction size)
@@ -90,6 +94,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -142,6 +161,16 @@ __device__ __forceinline__ void umma_commit_pred(uint32_t bar, uint32_t leader) 
       : "memory");
 }
 
+// commit that arrives on the same barrier offset in every CTA of `mask` (stage release of a multicast operand ring)
+__device__ __forceinline__ void umma_commit_mc_pred(uint32_t bar, uint16_t mask, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask), "r"(leader)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -171,6 +200,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // (x one of the 4 phases of the folded up-sampling conv); a CTA walks its items with the operand ring never draining
 // between items, and with two TMEM accumulator buffers so that the epilogue of item i (two groups of four warps,
 // alternating items) overlaps the TMA loads and MMAs of item i+1.
+#define ITG_UACC(slot, tvar) do { if (p.dbg) { const long long now_ = clock64(); dacc[slot] += (unsigned long long)(now_ - tvar); tvar = now_; } } while (0)
 constexpr int UMMA_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..7 / 8..11 epilogue groups
 constexpr int UMMA_BAR_BYTES = 1024;
 constexpr int UMMA_MAX_STAGES = 8;
@@ -202,7 +232,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, (uint32_t)p.cluster);   // every CTA of the cluster releases every stage (multicast commit)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
@@ -213,6 +243,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();           // peers' barriers are initialised before anybody multicasts into them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -223,9 +254,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int nphase = (p.mode == ITG_UPCONV) ? 4 : 1;
   const uint32_t buf_cols = p.tmem_cols >> 1;      // TMEM columns per accumulator buffer
 
-  // work item w -> (tile, phase, n block): n blocks of one tile run on neighbouring CTAs and share its A tiles in L2
+  // work item w -> (tile, phase, n block).  cluster == 1: n blocks of one tile run on neighbouring CTAs and share its A
+  // tiles in L2.  cluster > 1: a cluster walks the (tile, phase) items in lockstep, CTA rank r owns n block r and the
+  // activation tile of every k iteration is fetched ONCE (round-robin issuer) and multicast into all CTAs of the cluster.
+  const int crank = p.cluster > 1 ? (int)cluster_ctarank() : 0;
+  const int w_first = p.cluster > 1 ? (int)blockIdx.x / p.cluster : (int)blockIdx.x;
+  const int w_stride = p.cluster > 1 ? (int)gridDim.x / p.cluster : (int)gridDim.x;
+  const int w_limit = p.cluster > 1 ? p.nitems : p.nwork;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
   auto decode = [&](int w, int& tile, int& phase, int& n0) {
-    const int nb = w % p.nblocks, rest = w / p.nblocks;
+    int rest = w, nb = crank;
+    if (p.cluster == 1) { nb = w % p.nblocks; rest = w / p.nblocks; }
     n0 = nb * p.n_blk;
     phase = rest % nphase;
     tile = rest / nphase;
@@ -233,9 +272,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {                                                   // ---- TMA producer ----
-      int s = 0;
+      int s = 0, issuer = 0;
       uint32_t ph = 0;
-      for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+      unsigned long long dacc[2] = {0, 0};
+      long long tl = p.dbg ? clock64() : 0;
+      for (int w = w_first; w < w_limit; w += w_stride) {
         int tile, phase, n0;
         decode(w, tile, phase, n0);
         const int y0 = (tile / p.tiles_x) * th, x0 = (tile % p.tiles_x) * tw;
@@ -243,25 +284,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           int dy, dx, wt;
           tap_offsets(p.mode, phase, t, dy, dx, wt);
           for (int c = 0; c < p.nchunks; ++c) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);           // cluster > 1: ALL CTAs of the cluster have consumed this stage
+            ITG_UACC(0, tl);
             mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)(p.a_bytes + p.b_bytes));
             const uint32_t sa = stage0 + s * stage_bytes;
-            tma_load_3d(sa, &tm_a, bar_full + 8 * s, p.in_c_off + c * p.kc, x0 + dx + 1, y0 + dy + 1);
+            if (p.cluster == 1) {
+              tma_load_3d(sa, &tm_a, bar_full + 8 * s, p.in_c_off + c * p.kc, x0 + dx + 1, y0 + dy + 1);
+            } else {
+              if (issuer == crank)
+                tma_load_3d_mc(sa, &tm_a, bar_full + 8 * s, p.in_c_off + c * p.kc, x0 + dx + 1, y0 + dy + 1, cmask);
+              if (++issuer == p.cluster) issuer = 0;
+            }
             tma_load_2d(sa + p.a_stride, &tm_b, bar_full + 8 * s, c * p.kc, wt * p.n_pad + n0);
             if (++s == p.stages) { s = 0; ph ^= 1u; }
+            ITG_UACC(1, tl);
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = dacc[0]; p.dbg[1] = dacc[1]; }
     }
     __syncwarp();
   } else if (warp == 1) {                                              // ---- MMA warp: uniform control flow, one elected lane issues ----
     int s = 0, li = 0;
     uint32_t ph = 0;
-    for (int w = blockIdx.x; w < p.nwork; w += gridDim.x, ++li) {
+    unsigned long long dacc[3] = {0, 0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    for (int w = w_first; w < w_limit; w += w_stride, ++li) {
       const int b = li & 1;
       const uint32_t bph = (uint32_t)(li >> 1) & 1u;
       if (lane == 0) mbar_wait(bar_tempty + 8 * b, bph ^ 1u);          // the epilogue has drained this accumulator buffer
       __syncwarp();
+      ITG_UACC(0, tl);
       tc_fence_after();
       const uint32_t dcol = tmem_base + (uint32_t)b * buf_cols;
       int it = 0;
@@ -269,6 +322,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int c = 0; c < p.nchunks; ++c, ++it) {
           if (lane == 0) mbar_wait(bar_full + 8 * s, ph);
           __syncwarp();
+          ITG_UACC(1, tl);
           tc_fence_after();
           const uint32_t sa = stage0 + s * stage_bytes;
           const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
@@ -280,21 +334,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             umma_f16_pred(dcol, adesc + 2, bdesc + 2, p.idesc, 1u, (nk > 1) ? leader : 0u);
             umma_f16_pred(dcol, adesc + 4, bdesc + 4, p.idesc, 1u, (nk > 2) ? leader : 0u);
             umma_f16_pred(dcol, adesc + 6, bdesc + 6, p.idesc, 1u, (nk > 3) ? leader : 0u);
-            umma_commit_pred(bar_empty + 8 * s, leader);   // frees the stage when these MMAs have read it
+            if (p.cluster == 1) umma_commit_pred(bar_empty + 8 * s, leader);   // frees the stage when these MMAs have read it
+            else umma_commit_mc_pred(bar_empty + 8 * s, cmask, leader);        // ... in every CTA of the cluster
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
+          ITG_UACC(2, tl);
         }
       }
       umma_commit_pred(bar_tfull + 8 * b, elect_one_sync() ? 1u : 0u);   // accumulators of this item complete
       __syncwarp();
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = dacc[0]; p.dbg[3] = dacc[1]; p.dbg[4] = dacc[2]; }
   } else if (warp >= 4) {                                              // ---- epilogue: group g drains every second item ----
     const int g = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
     int li = g;
-    for (int w = blockIdx.x + g * gridDim.x; w < p.nwork; w += 2 * gridDim.x, li += 2) {
+    unsigned long long dacc[2] = {0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    for (int w = w_first + g * w_stride; w < w_limit; w += 2 * w_stride, li += 2) {
       int tile, phase, n0;
       decode(w, tile, phase, n0);
       const uint32_t bph = (uint32_t)(li >> 1) & 1u;
@@ -304,6 +363,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
       if (lane == 0) mbar_wait(bar_tfull + 8 * g, bph);
       __syncwarp();
+      ITG_UACC(0, tl);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)g * buf_cols;
       for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
@@ -324,11 +384,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(bar_tempty + 8 * g);
+      ITG_UACC(1, tl);
     }
+    if (p.dbg && blockIdx.x == 0 && ew == 0 && lane == 0) { p.dbg[5 + 2 * g] = dacc[0]; p.dbg[6 + 2 * g] = dacc[1]; }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();           // nobody exits while a peer may still multicast into / arrive on this CTA
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 

@@ -47,6 +47,29 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Same, as thread-block clusters of `cluster` CTAs along x (cluster == 1: plain launch).  The number of co-resident
+// clusters is bounded by the GPC layout; the grid is trimmed to what cudaOccupancyMaxActiveClusters reports.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  if (cluster <= 1) return launch_pdl(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+  static const bool no_pdl = getenv("ITG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 1 : 2;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) == cudaSuccess && max_clusters > 0 &&
+      (int)grid.x > max_clusters * cluster)
+    cfg.gridDim.x = (unsigned)(max_clusters * cluster);     // persistent kernel: fewer clusters just walk more items each
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -158,14 +181,24 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   p.tiles_x = (d.in_w + tw - 1) / tw;
   const int tiles_y = (d.in_h + th - 1) / th;
   p.n_pad = d.n_pad;
-  // N blocking: small grids (the 4x4 / 8x8 levels of a 7x21-patch texture have 19 / 74 M-tiles) are split along N
+  // N blocking: small grids (the 4x4 / 8x8 levels of a 7x21-patch texture have 21 / 74 M-tiles) are split along N
   // until the launch covers most of the SMs; every CTA then streams fewer weight bytes.  n_blk need not divide n_pad:
   // the last block computes (and its epilogue drops) columns past n_pad.
+  // ITG_CLUSTER=1 (opt-in): the N blocks of one (tile, phase) item run as ONE thread-block cluster and receive the
+  // item's activation tiles by TMA multicast (fetched once from L2).  Measured on B200 it is correct but not faster
+  // (cfg2 0.747 vs 0.722 ms, cfg3 45.4 vs 42.2 ms, cfg5band equal): these layers are not L2-bandwidth bound.
   const int phases = d.mode == ITG_UPCONV ? 4 : 1;
   const int m_ctas = p.tiles_x * tiles_y * phases;
-  int n_blk = d.n_pad > 256 ? ((d.n_pad + 1) / 2 + 15) / 16 * 16 : d.n_pad;
-  if (n_blk > 256) n_blk = 256;
-  {
+  static const bool use_cluster = getenv("ITG_CLUSTER") != nullptr;
+  int cl = 1, n_blk, nblocks;
+  if (use_cluster) {
+    while ((d.n_pad + cl - 1) / cl > 256) cl *= 2;                  // 416 -> 2 x 208, 832 -> 4 x 208
+    while (cl * 2 <= 8 && m_ctas * cl * 2 <= sm_count() + sm_count() / 8 && (d.n_pad + 2 * cl - 1) / (2 * cl) >= 24) cl *= 2;
+    n_blk = ((d.n_pad + cl - 1) / cl + 15) / 16 * 16;
+    nblocks = cl;
+  } else {
+    n_blk = d.n_pad > 256 ? ((d.n_pad + 1) / 2 + 15) / 16 * 16 : d.n_pad;
+    if (n_blk > 256) n_blk = 256;
     const int sms = sm_count();
     const int cand[] = {208, 128, 112, 96, 64, 48, 32};
     for (int c : cand) {
@@ -176,10 +209,12 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
       if (next > sms + sms / 8) break;                         // do not spill into a thin second wave
       n_blk = c;
     }
+    nblocks = (d.n_pad + n_blk - 1) / n_blk;
   }
-  const int nblocks = (d.n_pad + n_blk - 1) / n_blk;
   p.n_blk = n_blk;
   p.nblocks = nblocks;
+  p.cluster = cl;
+  p.nitems = m_ctas;
   p.nwork = m_ctas * nblocks;
   p.kc = d.k_pad >= 64 ? 64 : d.k_pad;
   p.nchunks = d.k_pad / p.kc;
@@ -237,11 +272,23 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   }
 
   const int smem = itg::UMMA_BAR_BYTES + stages * stage_bytes + 1024;
-  const int grid = p.nwork < sm_count() ? p.nwork : sm_count();
+  int grid = p.nwork < sm_count() ? p.nwork : sm_count();
+  if (p.cluster > 1) {
+    int nclusters = sm_count() / p.cluster;                // persistent: as many clusters as fit, each walking its items
+    if (nclusters > p.nitems) nclusters = p.nitems;
+    grid = nclusters * p.cluster;
+  }
   int flags = itg::EF_GENERIC;
   if (!d.mod_x && !d.out_f32 && d.res_kind != ITG_RES_F32) {
     if (d.out_img) flags = itg::EF_IMG;
     else flags = (d.res_kind == ITG_RES_GRID ? itg::EF_RES : 0) | (d.out_raw ? itg::EF_RAW : 0) | (d.out_act ? itg::EF_ACT : 0);
+  }
+  static const bool udbg_on = getenv("ITG_TILE_DBG") != nullptr;      // developer aid: per-role cycle counters, synchronous
+  static unsigned long long* udbg_buf = nullptr;
+  if (udbg_on) {
+    if (!udbg_buf) ITG_CUDA(cudaMalloc(&udbg_buf, 16 * sizeof(unsigned long long)));
+    ITG_CUDA(cudaMemsetAsync(udbg_buf, 0, 16 * sizeof(unsigned long long), st));
+    p.dbg = udbg_buf;
   }
 #define ITG_UMMA_LAUNCH(FL)                                                                                            \
   do {                                                                                                                 \
@@ -250,7 +297,7 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
       ITG_CUDA(cudaFuncSetAttribute(itg::conv_umma_kernel<T, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    ITG_CUDA(launch_pdl(itg::conv_umma_kernel<T, FL>, dim3(grid), dim3(itg::UMMA_THREADS), smem, st, tm_a, tm_b, p));  \
+    ITG_CUDA(launch_pdl_cluster(itg::conv_umma_kernel<T, FL>, dim3(grid), dim3(itg::UMMA_THREADS), smem, st, p.cluster, tm_a, tm_b, p)); \
   } while (0)
   {
     constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
@@ -265,6 +312,15 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
     }
   }
 #undef ITG_UMMA_LAUNCH
+  if (udbg_on) {
+    unsigned long long h[16];
+    ITG_CUDA(cudaStreamSynchronize(st));
+    ITG_CUDA(cudaMemcpy(h, udbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[itg umma dbg] mode=%d k=%d n_pad=%d n_blk=%d work=%d grid=%d stages=%d iters/item=%d flags=%d | kcycles CTA0: prod.wait_empty=%.1f prod.issue=%.1f "
+            "mma.wait_tempty=%.1f mma.wait_full=%.1f mma.issue=%.1f epi0.wait=%.1f epi0.work=%.1f epi1.wait=%.1f epi1.work=%.1f\n",
+            d.mode, d.k, d.n_pad, p.n_blk, p.nwork, grid, stages, total_iters, flags, h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3,
+            h[5] / 1e3, h[6] / 1e3, h[7] / 1e3, h[8] / 1e3);
+  }
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;
 }
