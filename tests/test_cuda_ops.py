@@ -262,3 +262,55 @@ def test_bad_arguments_raise(be):
         be.conv(op)
     with pytest.raises(L.ItgError, match="CUDA tensors"):
         L.ptr(torch.zeros(4))
+
+
+@pytest.mark.parametrize("mode_name,border", [("replicate", L.BORDER_REPLICATE), ("constant", L.BORDER_CONSTANT)])
+def test_halo_gather_indexing_is_bit_exact_vs_reference_local_padder(be, mode_name, border):
+    """The conv kernels' neighbourhood gather == models.layers.LocalPadder windows, bit for bit.
+
+    tests/golden/localpad.npz holds integer-coded patch batches and the (B, C, r+2, r+2) windows the UNMODIFIED
+    reference LocalPadder produced for them.  A 3x3 conv whose weight for output column t*C+c is the delta at tap t,
+    channel c copies the gathered neighbourhood to its output: out[y, x, t*C + c] = window[c, y%r + t//3, x%r + t%3].
+    fp32 CUDA-core kernel on the golden integers; tcgen05 halo-tile and streaming kernels (fp16 holds integers < 2048
+    exactly) on the same values reduced mod 2039, all compared exactly."""
+    import os
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "localpad.npz"))
+    x = torch.from_numpy(d[f"{mode_name}_0_in"])            # first sub-image: pure outer padding ('1st_row_1st_col')
+    win = torch.from_numpy(d[f"{mode_name}_0_out"])          # (9, C, r+2, r+2)
+    B, C, r, _ = x.shape
+    nph = npw = 3
+    H, W = nph * r, npw * r
+    merged = x.reshape(nph, npw, C, r, r).permute(2, 0, 3, 1, 4).reshape(C, H, W)
+    # delta weights: (9*C, C, 3, 3)
+    wt = torch.zeros(9 * C, C, 3, 3)
+    for t in range(9):
+        for c in range(C):
+            wt[t * C + c, c, t // 3, t % 3] = 1.0
+    ref = torch.empty(H, W, 9 * C)
+    for p in range(B):
+        py, px = p // npw, p % npw
+        for t in range(9):
+            ref[py * r:(py + 1) * r, px * r:(px + 1) * r, t * C:(t + 1) * C] = \
+                win[p, :, t // 3:t // 3 + r, t % 3:t % 3 + r].permute(1, 2, 0)
+    for precision, impl, modulo in (("fp32", L.IMPL_DIRECT, None), ("fp16", L.IMPL_TILE, 2039), ("fp16", L.IMPL_UMMA, 2039),
+                                    ("bf16", L.IMPL_TILE, 251)):
+        dtype = DT[precision]
+        src_v = merged if modulo is None else torch.remainder(merged, modulo)
+        ref_v = ref if modulo is None else torch.remainder(ref, modulo)
+        if modulo is not None and border == L.BORDER_CONSTANT:
+            ref_v = torch.where(ref == 0, torch.zeros_like(ref_v), ref_v)        # padding zeros stay zeros
+        kin = c_store(C)
+        buf = torch.full((H + 2, W + 2, kin), -7.0)
+        buf[1:-1, 1:-1, :C] = src_v.permute(1, 2, 0)
+        buf[1:-1, 1:-1, C:] = 0
+        g = Grid(buf.to(dtype).cuda(), H, W, kin)
+        be.fill_frame(g, border)                                                   # F.pad of layers.py:82
+        w = PK.pack_conv3x3(wt, dtype).cuda()
+        out = Grid(torch.zeros((H + 2, W + 2, c_store(9 * C)), dtype=dtype, device="cuda"), H, W, c_store(9 * C))
+        op = ConvOp(mode=L.CONV3X3, src=g, w=w, k=kin, bias=None, impl=impl, name="gather")
+        op.out_h, op.out_w, op.out_c, op.out_raw = H, W, c_store(9 * C), out
+        be.conv(op)
+        torch.cuda.synchronize()
+        got = out.interior[..., :9 * C].float().cpu()
+        assert torch.equal(got, ref_v), (precision, impl, (got - ref_v).abs().max().item())
