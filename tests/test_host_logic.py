@@ -150,3 +150,22 @@ def test_cli_keeps_the_reference_flags():
     load_G({"module." + k: v for k, v in sd.items()}, net)          # DataParallel checkpoints
     assert not net.training
     assert torch.equal(net.state_dict()["start.conv.weight"], sd["start.conv.weight"])
+
+
+@pytest.mark.parametrize("nps,H,W", [(4, 224, 320), (5, 288, 416), (3, 150, 200)])
+def test_sequential_protocol_other_subimage_sizes(nps, H, W):
+    """The reference sampler takes num_patches_height/width (utils.py:258-259); square sub-images of 3..5 patches,
+    sizes that are not multiples of the patch, gamma != 0: equal to the oracle's restatement of the shipped schedule."""
+    kw = dict(z_dim=16, G_ch=8, n_layers_G=4, attention=True, leak=0.02, type_norm="BN", outer_padding="replicate")
+    ocfg = O.GenCfg(**kw, num_patches_h=nps, num_patches_w=nps)
+    sd = O.make_state_dict(ocfg, 5, stress=True)
+    geo = O.geometry(H, W, ocfg)
+    z, _ = O.make_noise(ocfg, geo["total_h"], geo["total_w"], 3)
+    with torch.no_grad():
+        ref = O.sample_patch_by_patch(sd, ocfg, H, W, z)
+    net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
+    got = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=16, num_patches_height=nps, num_patches_width=nps,
+                                                      output_resolution_height=H, output_resolution_width=W,
+                                                      schedule="sequential", noise=(z, None))
+    assert tuple(got.shape) == (1, 3, H, W)
+    assert (got - ref).abs().max().item() <= 5e-5
