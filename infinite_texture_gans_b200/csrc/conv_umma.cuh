@@ -366,6 +366,52 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ITG_UACC(0, tl);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)g * buf_cols;
+      // interior tile (all pixels valid, none on the image border) with a specialised epilogue: addresses are formed once
+      // per pixel and no frame logic runs; border tiles and the generic / SSM / image epilogues take the general path
+      const int ty0 = (tile / p.tiles_x) * th, tx0 = (tile % p.tiles_x) * tw;
+      const bool interior = (F & (EF_GENERIC | EF_IMG)) == 0 && ty0 > 0 && tx0 > 0 && ty0 + th < p.m_h && tx0 + tw < p.m_w;
+      if (interior) {
+        const EpiParams& ep = p.ep;
+        const size_t off = grid_off(oy, ox, ep.out_w, ep.out_c, 0);
+        const T* rp = (F & EF_RES) ? reinterpret_cast<const T*>(ep.res) + grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, 0) : nullptr;
+        for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = n0 + c0 + 8 * h;
+            if (ch >= ep.out_c) continue;
+            float x8[8];
+            const float4 ba = *reinterpret_cast<const float4*>(ep.bias + ch), bb = *reinterpret_cast<const float4*>(ep.bias + ch + 4);
+            x8[0] = v[8 * h] + ba.x; x8[1] = v[8 * h + 1] + ba.y; x8[2] = v[8 * h + 2] + ba.z; x8[3] = v[8 * h + 3] + ba.w;
+            x8[4] = v[8 * h + 4] + bb.x; x8[5] = v[8 * h + 5] + bb.y; x8[6] = v[8 * h + 6] + bb.z; x8[7] = v[8 * h + 7] + bb.w;
+            if (F & EF_RES) {
+              float r8[8];
+              load8(rp + ch, r8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x8[i] += r8[i];
+            }
+            if (F & EF_RAW) store8(reinterpret_cast<T*>(ep.out_raw) + off + ch, x8);
+            if (F & EF_ACT) {
+              float w8[8];
+              if (ep.scale != nullptr) {
+                const float4 sa = *reinterpret_cast<const float4*>(ep.scale + ch), sb = *reinterpret_cast<const float4*>(ep.scale + ch + 4);
+                const float4 ta = *reinterpret_cast<const float4*>(ep.shift + ch), tb = *reinterpret_cast<const float4*>(ep.shift + ch + 4);
+                w8[0] = fmaf(sa.x, x8[0], ta.x); w8[1] = fmaf(sa.y, x8[1], ta.y); w8[2] = fmaf(sa.z, x8[2], ta.z); w8[3] = fmaf(sa.w, x8[3], ta.w);
+                w8[4] = fmaf(sb.x, x8[4], tb.x); w8[5] = fmaf(sb.y, x8[5], tb.y); w8[6] = fmaf(sb.z, x8[6], tb.z); w8[7] = fmaf(sb.w, x8[7], tb.w);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w8[i] = x8[i];
+              }
+              if (!ep.act_linear) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w8[i] = act_fn(w8[i], ep.leak);
+              }
+              store8(reinterpret_cast<T*>(ep.out_act) + off + ch, w8);
+            }
+          }
+        }
+      } else
       for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
