@@ -155,16 +155,6 @@ def run_reference(args, kw, th, tw, desc):
 # --------------------------------------------------------------------------------------------------
 # per-launch roofline of the conv kernel
 # --------------------------------------------------------------------------------------------------
-def conv_flops(op) -> float:
-    """Algorithmic FLOPs (2*MAC of the reference's arithmetic) of one conv launch."""
-    from infinite_texture_gans_b200 import _lib as L
-    n = op.out_c if op.out_img is None else op.img_c
-    n_real = getattr(op, "_n_real", None) or n
-    k_real = getattr(op, "_k_real", None) or op.k
-    taps = 1 if op.mode == L.CONV1X1 else 9
-    return 2.0 * taps * k_real * n_real * op.out_h * op.out_w
-
-
 def launch_profile(plan, reps=5):
     """CUDA-event time of every launch of the plan (eager, same stream), median of `reps`."""
     n = plan.n_launches

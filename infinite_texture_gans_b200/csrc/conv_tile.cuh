@@ -17,6 +17,7 @@
 //     mode and the epilogue variant are template parameters: measured on B200, the single-thread issue loop of
 //     the first version cost ~320 cycles per tcgen05.mma and was the bottleneck (profiles/r01_notes.md).
 #pragma once
+#include <type_traits>
 #include "conv_umma.cuh"
 
 namespace itg {
@@ -290,6 +291,11 @@ conv_tile_kernel(const TileParams p) {
       rs[i] = (fast && n16) ? vec[64 + i] : 1.f;
       rt[i] = (fast && n16) ? vec[192 + i] : 0.f;
     }
+    unsigned long long rb2[8], rs2[8], rt2[8];           // the same, packed two channels wide for FADD2 / FFMA2
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { rb2[i] = pk2(rb[2 * i], rb[2 * i + 1]); rs2[i] = pk2(rs[2 * i], rs[2 * i + 1]); rt2[i] = pk2(rt[2 * i], rt[2 * i + 1]); }
+    const bool leak01 = ep.leak >= 0.f && ep.leak <= 1.f;     // leaky(x) == max(x, leak * x)
+    const unsigned long long leak2 = pk2(ep.leak, ep.leak);
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
     const int nbuf_log2 = p.nbuf == 4 ? 2 : 1;
@@ -342,29 +348,37 @@ conv_tile_kernel(const TileParams p) {
             }
             continue;
           }
-          if (F & EF_RES) {
-            float r[16];
-            if (PRE) {
-              Vec8<T> t0 = *reinterpret_cast<const Vec8<T>*>(&pre[0]);
-              Vec8<T> t1 = *reinterpret_cast<const Vec8<T>*>(&pre[1]);
+          unsigned long long v2[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { r[i] = Op<T>::to_f(t0.v[i]); r[8 + i] = Op<T>::to_f(t1.v[i]); }
+          for (int i = 0; i < 8; ++i) v2[i] = pk2(v[2 * i], v[2 * i + 1]);
+          if (F & EF_RES) {
+            if (PRE) {
+              const __half2* h0 = reinterpret_cast<const __half2*>(&pre[0]);
+              const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&pre[0]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {                                    // pre[0], pre[1] are adjacent: 8 channel pairs
+                float2 f;
+                if (sizeof(T) == 2 && std::is_same<T, __half>::value) f = __half22float2(h0[i]);
+                else f = __bfloat1622float2(b0[i]);
+                v2[i] = add2(v2[i], pk2(f.x, f.y));
+              }
             } else {
               const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, 0);
               float r0[8], r1[8];
               load8(rp, r0);
               load8(rp + 8, r1);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { r[i] = r0[i]; r[8 + i] = r1[i]; }
+              for (int i = 0; i < 4; ++i) { v2[i] = add2(v2[i], pk2(r0[2 * i], r0[2 * i + 1])); v2[4 + i] = add2(v2[4 + i], pk2(r1[2 * i], r1[2 * i + 1])); }
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += r[i];
           }
           const size_t off = grid_off(oy, ox, ep.out_w, ep.out_c, 0);
           if (F & EF_RAW) {
             float w0[8], w1[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { w0[i] = v[i] + rb[i]; w1[i] = v[8 + i] + rb[8 + i]; }
+            for (int i = 0; i < 4; ++i) {
+              unpk2(add2(v2[i], rb2[i]), w0[2 * i], w0[2 * i + 1]);
+              unpk2(add2(v2[4 + i], rb2[4 + i]), w1[2 * i], w1[2 * i + 1]);
+            }
             T* o = reinterpret_cast<T*>(ep.out_raw) + off;
             store8(o, w0);
             if (ep.out_c > 8) store8(o + 8, w1);
@@ -372,10 +386,19 @@ conv_tile_kernel(const TileParams p) {
           if (F & EF_ACT) {
             float w0[8], w1[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { w0[i] = fmaf(rs[i], v[i], rt[i]); w1[i] = fmaf(rs[8 + i], v[8 + i], rt[8 + i]); }
-            if (!ep.act_linear) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { w0[i] = act_fn(w0[i], ep.leak); w1[i] = act_fn(w1[i], ep.leak); }
+            for (int i = 0; i < 8; ++i) {
+              unsigned long long y2 = fma2(rs2[i], v2[i], rt2[i]);
+              float ya, yb;
+              if (!ep.act_linear && leak01) {
+                float la, lb;
+                unpk2(mul2(y2, leak2), la, lb);
+                unpk2(y2, ya, yb);
+                ya = fmaxf(ya, la); yb = fmaxf(yb, lb);
+              } else {
+                unpk2(y2, ya, yb);
+                if (!ep.act_linear) { ya = act_fn(ya, ep.leak); yb = act_fn(yb, ep.leak); }
+              }
+              if (i < 4) { w0[2 * i] = ya; w0[2 * i + 1] = yb; } else { w1[2 * (i - 4)] = ya; w1[2 * (i - 4) + 1] = yb; }
             }
             T* o = reinterpret_cast<T*>(ep.out_act) + off;
             store8(o, w0);
