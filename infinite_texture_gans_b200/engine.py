@@ -350,25 +350,30 @@ class Plan:
     # buffers and compiled launch list
     # ------------------------------------------------------------------------------------------
     def _materialise(self, reuse: bool):
-        # liveness-based first-fit arena: a grid tensor's bytes are reused once its last reader has run
-        order = sorted(self._vgrids, key=lambda v: v.first)
-        blocks: List[List[int]] = []      # [offset, size, free_after_step]
-        total = 0
+        # liveness-based arena: tensors whose lifetimes [first, last] do not overlap may share bytes.  Offsets are
+        # assigned greedily by decreasing size (the large full-resolution tensors come last in the network, so a
+        # first-come first-fit wastes most of the reuse): each tensor takes the lowest offset that does not collide
+        # with an already placed tensor alive at the same time.
         offs: Dict[int, int] = {}
-        for v in order:
-            need = (v.nbytes + ALIGN - 1) // ALIGN * ALIGN
-            slot = None
-            if reuse:
-                for blk in blocks:
-                    if blk[2] < v.first and blk[1] >= need and (slot is None or blk[1] < slot[1]):
-                        slot = blk
-            if slot is None:
-                slot = [total, need, v.last]
-                blocks.append(slot)
+        total = 0
+        if reuse:
+            placed: List[Tuple[int, int, int, int]] = []          # (offset, size, first, last)
+            for v in sorted(self._vgrids, key=lambda v: -v.nbytes):
+                need = (v.nbytes + ALIGN - 1) // ALIGN * ALIGN
+                busy = sorted((o, o + sz) for o, sz, f, l in placed if not (l < v.first or f > v.last))
+                off = 0
+                for lo, hi in busy:
+                    if off + need <= lo:
+                        break
+                    off = max(off, hi)
+                placed.append((off, need, v.first, v.last))
+                offs[id(v)] = off
+                total = max(total, off + need)
+        else:
+            for v in self._vgrids:
+                need = (v.nbytes + ALIGN - 1) // ALIGN * ALIGN
+                offs[id(v)] = total
                 total += need
-            else:
-                slot[2] = v.last
-            offs[id(v)] = slot[0]
         self.arena = torch.empty(total + ALIGN, dtype=torch.uint8, device=self.device)
         base_off = (-self.arena.data_ptr()) % ALIGN if self.arena.is_cuda else 0
         self.arena_bytes = total
