@@ -173,3 +173,66 @@ def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, nu
         LocalPadder.num_patches_h, LocalPadder.num_patches_w = saved
     img = canvas[:, :, :H, :W]
     return img if return_on_device else img.cpu()
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming: many textures, copies overlapped with compute
+# ------------------------------------------------------------------------------------------------
+class HostOutputPipe:
+    """Multi-buffered device -> pinned-host hand-off of finished images.  `push(img)` snapshots the device image
+    (device-to-device, on the current stream) and starts its copy to pinned host memory on a side stream, so the next
+    Generator pass runs while the previous image crosses PCIe; `wait(slot)` blocks until that image is on the host.
+    A slot's host tensor is overwritten `depth` pushes later."""
+
+    def __init__(self, shape, device, depth: int = 3):
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device)
+        self.stage = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.host = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]      # image of the slot is complete in self.stage
+        self.done = [torch.cuda.Event() for _ in range(depth)]       # ... and in self.host
+        self.k = 0
+
+    def push(self, img: torch.Tensor) -> int:
+        s = self.k % self.depth
+        self.k += 1
+        cur = torch.cuda.current_stream()
+        if self.k > self.depth:
+            cur.wait_event(self.done[s])                             # the slot's previous image has left the device
+        self.stage[s].copy_(img)                                     # after this the engine may overwrite its output buffer
+        self.ready[s].record(cur)
+        self.copy_stream.wait_event(self.ready[s])
+        with torch.cuda.stream(self.copy_stream):
+            self.host[s].copy_(self.stage[s], non_blocking=True)
+            self.done[s].record(self.copy_stream)
+        return s
+
+    def wait(self, slot: int) -> torch.Tensor:
+        self.done[slot].synchronize()
+        return self.host[slot]
+
+
+def generate_textures(netG, noises, output_resolution_height: int, output_resolution_width: int, base_res: int = 4,
+                      num_patches_height: int = 3, num_patches_width: int = 3, graph: bool = True):
+    """Iterator over host-resident (1, img_ch, H, W) fp32 textures, one per element of `noises`
+    (each `(z_full, maps_full)` as drawn by `draw_noise`, ideally in pinned memory).  Same result per texture as
+    `sample_from_gen_PatchByPatch_test(..., noise=...)` with the one-shot schedule; the difference is that texture k's
+    copy to the host overlaps the Generator pass of texture k+1.  A yielded tensor is a view of a pinned staging buffer
+    and stays valid until the iterator is advanced again."""
+    G = _unwrap(netG)
+    geo = patch_grid_geometry(output_resolution_height, output_resolution_width, G.n_layers_G, base_res,
+                              num_patches_height, num_patches_width)
+    H, W = output_resolution_height, output_resolution_width
+    dev = next(G.parameters()).device
+    pipes = G.__dict__.setdefault("_host_pipes", {})     # pinned staging buffers are expensive to allocate: keep them per output size
+    pipe = pipes.get((H, W, dev))
+    if pipe is None:
+        pipe = pipes[(H, W, dev)] = HostOutputPipe((1, G.img_ch, H, W), dev)
+    in_flight = []                                       # at most depth - 1 images between the Generator pass and the consumer
+    for z_full, maps_full in noises:
+        img = generate_full_grid(netG, z_full[:1], None if maps_full is None else [m[:1] for m in maps_full], graph=graph)
+        in_flight.append(pipe.push(img[:, :, :H, :W]))
+        if len(in_flight) == pipe.depth:
+            yield pipe.wait(in_flight.pop(0))
+    for slot in in_flight:
+        yield pipe.wait(slot)

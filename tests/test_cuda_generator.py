@@ -84,6 +84,27 @@ def test_cuda_graph_replay_is_bit_identical():
     assert torch.equal(a, b) and torch.equal(b, c)
 
 
+@pytest.mark.parametrize("name", ["gen_bn5_gamma0_rep", "gen_ssm4_att_rep"])
+def test_streaming_textures_equal_blocking_sampler(name):
+    """utils.generate_textures (copies overlapped with compute, double-buffered) returns, texture by texture, exactly what
+    the blocking sampler returns for the same noise -- including a crop that is not a multiple of the patch size."""
+    import infinite_texture_gans_b200 as itg
+    d, kw, ocfg, sd, z, maps = load_case(name)
+    net = make_generator(kw, sd, "fp16", "cuda")
+    H, W = int(d["H"]) - 5, int(d["W"]) - 9
+    g = torch.Generator().manual_seed(7)
+    noises = [(z, maps)]
+    for _ in range(4):
+        noises.append((torch.randn(z.shape, generator=g), None if maps is None else [torch.randn(m.shape, generator=g) for m in maps]))
+    want = [itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], output_resolution_height=H, output_resolution_width=W,
+                                                        noise=n).clone() for n in noises]
+    got = [img.clone() for img in itg.utils.generate_textures(net, iter(noises), H, W)]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.shape == (1, kw.get("img_ch", 3), H, W) and torch.equal(a, b)
+    assert not torch.equal(got[0], got[1])
+
+
 @pytest.mark.parametrize("kw,th,tw", [
     (dict(z_dim=128, G_ch=52, n_layers_G=6, attention=True, leak=0.02, type_norm="BN", outer_padding="replicate"), 2, 4),
     (dict(z_dim=128, G_ch=52, n_layers_G=5, attention=True, leak=0.02, type_norm="SSM", outer_padding="replicate"), 3, 3),
