@@ -26,11 +26,21 @@ constexpr int TILE_W = 8, TILE_H = 16;                       // output tile = 12
 constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;      // input neighbourhood
 constexpr int HALO_PX = HALO_W * HALO_H;                     // 180
 constexpr int PLANE_BYTES = HALO_PX * 16;                    // one 8-channel plane of the halo tile: 2880 B
-constexpr int TILE_EPI_GROUPS = 2;          // epilogue groups of four warps; group g drains tiles it = g (mod 4)
-constexpr int TILE_THREADS = 32 * (4 + 4 * TILE_EPI_GROUPS + 1);   // warps 0,2,last: producers; 1,3: MMA issuers; 4..4+4G-1: epilogue
-constexpr int TILE_HDR_BYTES = 1536;       // barriers + per-channel epilogue vectors (bias | scale | shift | scale*bias+shift)
-constexpr int TILE_MAX_STAGES = 12;
-constexpr int TILE_PWARPS = 3;              // producer warps 0, 2, 3: each loads every third tile on its own
+#ifndef ITG_TILE_EPI_GROUPS
+#define ITG_TILE_EPI_GROUPS 4
+#endif
+// Warp roles: warps 0..NM-1 issue MMAs (one per scheduler), warps 4..4+4G-1 are G epilogue groups of four warps (TMEM lane
+// quarter = warp % 4), the three producers are the remaining warps below 4 plus the warps after the epilogue groups.
+// MMA warp m and epilogue group m work on the same tiles (it = m mod NM) and so form independent pipelines.
+constexpr int TILE_EPI_GROUPS = ITG_TILE_EPI_GROUPS;
+constexpr int TILE_MMA_WARPS = TILE_EPI_GROUPS;
+constexpr int TILE_PWARPS = 3;              // producer warps: each loads every third tile on its own
+constexpr int TILE_WARPS = 4 + 4 * TILE_EPI_GROUPS + (TILE_PWARPS - (4 - TILE_MMA_WARPS));
+constexpr int TILE_THREADS = 32 * TILE_WARPS;
+constexpr int TILE_HDR_BYTES = 2048;       // barriers + per-channel epilogue vectors (bias | scale | shift | scale*bias+shift)
+constexpr int TILE_MAX_STAGES = 24;
+constexpr int TILE_MAX_NBUF = 8;            // TMEM accumulator buffers
+constexpr int TILE_VEC_OFF = 576;           // header: full[24] | empty[24] | tfull[8] | tempty[8] | tmem slot | vectors (1 KB)
 
 struct TileParams {
   int m_h, m_w;            // M-grid size (input interior)
@@ -120,17 +130,17 @@ conv_tile_kernel(const TileParams p) {
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t bar_full = sbase;                    // [stages <= 12]
-  const uint32_t bar_empty = sbase + 128;             // [stages <= 12]
-  const uint32_t bar_tfull = sbase + 256;             // [nbuf <= 4] accumulator buffer complete
-  const uint32_t bar_tempty = sbase + 288;            // [nbuf <= 4] accumulator buffer drained
-  const uint32_t tmem_slot = sbase + 320;
-  float* vec = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + 384);   // bias | scale | shift, 64 floats each
+  const uint32_t bar_full = sbase;                    // [stages <= 24]
+  const uint32_t bar_empty = sbase + 192;             // [stages <= 24]
+  const uint32_t bar_tfull = sbase + 384;             // [nbuf <= 8] accumulator buffer complete
+  const uint32_t bar_tempty = sbase + 448;            // [nbuf <= 8] accumulator buffer drained
+  const uint32_t tmem_slot = sbase + 512;
+  float* vec = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + TILE_VEC_OFF);   // bias | scale | shift | folded, 64 floats each
   const uint32_t w_smem = sbase + TILE_HDR_BYTES;
   const uint32_t a_smem = w_smem + (uint32_t)p.w_bytes;
 
   pdl_launch_dependents();
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(bar_full + 8 * i, 32);
       mbar_init(bar_empty + 8 * i, 1);
@@ -141,7 +151,7 @@ conv_tile_kernel(const TileParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 4) tmem_alloc(tmem_slot, p.tmem_cols);
 
   // ---- park the weights of every tap in shared memory: image [tap][k-group][n][8 channels] ----
   {
@@ -173,8 +183,8 @@ conv_tile_kernel(const TileParams p) {
   // Loop bookkeeping without integer division: ring positions advance by a fixed step, tile coordinates by a
   // precomputed (dy, dx) with carry.  mbarrier waits are done by lane 0 only (a 32-lane try_wait on one barrier
   // measured ~300 cycles even when already complete) followed by __syncwarp.
-  if (warp == 0 || warp == 2 || warp == 4 + 4 * TILE_EPI_GROUPS) {                // ---- producers ----
-    const int pw = warp == 0 ? 0 : (warp == 2 ? 1 : 2);            // producer warp 0..2 loads tiles it = 3k + pw, all 32 lanes on one tile
+  if ((warp >= TILE_MMA_WARPS && warp < 4) || warp >= 4 + 4 * TILE_EPI_GROUPS) {  // ---- producers ----
+    const int pw = warp < 4 ? warp - TILE_MMA_WARPS : (4 - TILE_MMA_WARPS) + warp - (4 + 4 * TILE_EPI_GROUPS);   // producer 0..2 loads tiles it = 3k + pw, all 32 lanes on one tile
     const int kg_log2 = 31 - __clz(p.kg);
     const int cg_total = p.in_c >> 3;
     const T* in = reinterpret_cast<const T*>(p.in);
@@ -235,17 +245,19 @@ conv_tile_kernel(const TileParams p) {
       s_pub += TILE_PWARPS; if (s_pub >= p.stages) s_pub -= p.stages;
     }
     if (p.dbg && pw == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_acc[i];
-  } else if (warp == 1 || warp == 3) {                                         // ---- two MMA warps (uniform; one lane issues), alternate tiles ----
-    const int mw = warp >> 1;
+  } else if (warp < TILE_MMA_WARPS) {                                          // ---- MMA warps (uniform; one lane issues), tiles it = mw (mod NM) ----
+    const int mw = warp;
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
     const int ksteps = p.kg >> 1;
     const uint32_t w16 = w_smem >> 4, n16 = (uint32_t)p.n;                     // weight image: 16 B per (k-group, n)
-    const int nbuf_log2 = p.nbuf == 4 ? 2 : 1;
+    const int nbuf_log2 = 31 - __clz(p.nbuf);
+    // an accumulator buffer must belong to ONE MMA warp / epilogue group (parity waits), so no more of them than buffers
+    const int nm = p.nbuf < TILE_MMA_WARPS ? p.nbuf : TILE_MMA_WARPS;
     int s = mw % p.stages;
     uint32_t ph = (uint32_t)(mw / p.stages) & 1u;
     int it = mw;
-    for (int tile = blockIdx.x + mw * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
+    for (int tile = mw < nm ? blockIdx.x + mw * (int)gridDim.x : p.ntiles; tile < p.ntiles; tile += nm * gridDim.x, it += nm) {
       const int b = it & (p.nbuf - 1);
       const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
       if (lane == 0) {
@@ -268,7 +280,7 @@ conv_tile_kernel(const TileParams p) {
       }
       __syncwarp();
       ITG_ACC(2, tl);
-      s += 2; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+      s += nm; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
     }
     if (p.dbg && lane == 0 && mw == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i];
   } else if (warp >= 4 && warp < 4 + 4 * TILE_EPI_GROUPS) {                    // ---- epilogue ----
@@ -277,13 +289,13 @@ conv_tile_kernel(const TileParams p) {
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
     const EpiParams& ep = p.ep;
-    const uint32_t vec_smem = sbase + 384;              // bias | scale | shift copies (see load_vec8)
+    const uint32_t vec_smem = sbase + TILE_VEC_OFF;     // bias | scale | shift copies (see load_vec8)
     // Fast path (n == 16, tile not touching the image border, specialised epilogue): bias / BN scale / folded shift of the
     // 16 channels live in registers, addresses are formed once per pixel, no frame logic.  ~100 instead of ~250
     // instructions per pixel; everything else takes the general path below.
     constexpr bool FASTF = (F & EF_GENERIC) == 0;
     const bool fast = FASTF && ((F & EF_IMG) != 0 || ep.out_c <= p.n);
-    const bool n16 = p.n == 16;
+    const bool n16 = p.n == 16 && TILE_EPI_GROUPS <= 2;    // (more groups = fewer registers per thread: vectors stay in shared memory)
     float rb[16], rs[16], rt[16];                        // n == 16: the vectors stay in registers
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -298,7 +310,7 @@ conv_tile_kernel(const TileParams p) {
     const unsigned long long leak2 = pk2(ep.leak, ep.leak);
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
-    const int nbuf_log2 = p.nbuf == 4 ? 2 : 1;
+    const int nbuf_log2 = 31 - __clz(p.nbuf);
     // a group may wait at most one barrier phase ahead (parity waits), so no more groups than accumulator buffers
     const int ngroups = p.nbuf < TILE_EPI_GROUPS ? p.nbuf : TILE_EPI_GROUPS;
     const int step = ngroups * (int)gridDim.x;
@@ -306,19 +318,49 @@ conv_tile_kernel(const TileParams p) {
     int tile = g < ngroups ? blockIdx.x + g * (int)gridDim.x : p.ntiles;
     int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     int it = g;
+    constexpr bool PRE = (F & EF_GENERIC) == 0 && (F & EF_RES) != 0 && NPHASE == 1;
+    // pixels of 16 k channels are 32-byte aligned: 256-bit loads / stores, one per 16 channels
+    const bool wide = sizeof(T) == 2 && (ep.out_c & 15) == 0 && (!(F & EF_RES) || (ep.res_c & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(ep.out_raw) | reinterpret_cast<uintptr_t>(ep.out_act) | reinterpret_cast<uintptr_t>(ep.res)) & 31) == 0;
+    const bool pipe_res = PRE && n16;
+    uint4 nxt[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (pipe_res && tile < p.ntiles) {
+      const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
+      if (y < p.m_h && x < p.m_w) {
+        const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(y >> ep.res_shift, x >> ep.res_shift, ep.res_w, ep.res_c, 0);
+        nxt[0] = *reinterpret_cast<const uint4*>(rp);
+        if (ep.out_c > 8) nxt[1] = *reinterpret_cast<const uint4*>(rp + 8);
+      }
+    }
     for (; tile < p.ntiles; tile += step, it += ngroups) {
       const int b = it & (p.nbuf - 1);
       const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
       const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
       const bool valid = (y < p.m_h) && (x < p.m_w);
-      // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier
+      // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier -- and, for the
+      // 16-channel layers, one whole tile ahead (nxt), so that their latency never sits between two tiles
       uint4 pre[8];
-      constexpr bool PRE = (F & EF_GENERIC) == 0 && (F & EF_RES) != 0 && NPHASE == 1;
-      if (PRE && valid) {
+      if (PRE && pipe_res) {
+        pre[0] = nxt[0]; pre[1] = nxt[1];
+        int nty = ty + sdy, ntx = tx + sdx;
+        if (ntx >= p.tiles_x) { ntx -= p.tiles_x; ++nty; }
+        const int ny = nty * TILE_H + (row >> 3), nx = ntx * TILE_W + (row & 7);
+        if (tile + step < p.ntiles && ny < p.m_h && nx < p.m_w) {
+          const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(ny >> ep.res_shift, nx >> ep.res_shift, ep.res_w, ep.res_c, 0);
+          nxt[0] = *reinterpret_cast<const uint4*>(rp);
+          if (ep.out_c > 8) nxt[1] = *reinterpret_cast<const uint4*>(rp + 8);
+        }
+      } else if (PRE && valid) {
         const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(y >> ep.res_shift, x >> ep.res_shift, ep.res_w, ep.res_c, 0);
+        if (wide) {                                                              // 16 channels (32 B) per load
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 8 < p.n && i * 8 < ep.out_c) pre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+          for (int i = 0; i < 4; ++i)
+            if (i * 16 < p.n && i * 16 < ep.out_c) ldg256(rp + i * 16, pre[2 * i], pre[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i * 8 < p.n && i * 8 < ep.out_c) pre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+        }
       }
       if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);
       __syncwarp();
@@ -440,6 +482,49 @@ conv_tile_kernel(const TileParams p) {
             if (c0 >= p.n) break;
             float v[16];
             tmem_ld16(trow + (uint32_t)c0, v);
+            if (wide && c0 < ep.out_c) {                                       // 16 channels: one 256-bit store per output tensor
+              uint32_t rw[8], aw[8];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t o4 = vec_smem + (uint32_t)((c0 + 8 * h) * 4);
+                float b8[8], x8[8];
+                {
+                  const float4 ba = lds_f4(o4), bb = lds_f4(o4 + 16);
+                  b8[0] = ba.x; b8[1] = ba.y; b8[2] = ba.z; b8[3] = ba.w; b8[4] = bb.x; b8[5] = bb.y; b8[6] = bb.z; b8[7] = bb.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x8[i] = v[8 * h + i];
+                if (F & EF_RES) {
+                  uint4 rr;
+                  if (PRE) rr = pre[2 * cc + h];
+                  else rr = *reinterpret_cast<const uint4*>(rp + c0 + 8 * h);
+                  Vec8<T> t0 = *reinterpret_cast<const Vec8<T>*>(&rr);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) x8[i] += Op<T>::to_f(t0.v[i]);
+                }
+                if (F & EF_RAW) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) rw[4 * h + i] = pack2<T>(x8[2 * i] + b8[2 * i], x8[2 * i + 1] + b8[2 * i + 1]);
+                }
+                if (F & EF_ACT) {
+                  const float4 sa = lds_f4(o4 + 256), sb = lds_f4(o4 + 272), ta = lds_f4(o4 + 768), tb = lds_f4(o4 + 784);
+                  const float s8[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                  const float t8[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                  float w8[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) w8[i] = fmaf(s8[i], x8[i], t8[i]);
+                  if (!ep.act_linear) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w8[i] = act_fn(w8[i], ep.leak);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) aw[4 * h + i] = pack2<T>(w8[2 * i], w8[2 * i + 1]);
+                }
+              }
+              if (F & EF_RAW) stg256(reinterpret_cast<T*>(ep.out_raw) + off + c0, rw);
+              if (F & EF_ACT) stg256(reinterpret_cast<T*>(ep.out_act) + off + c0, aw);
+              continue;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {                                      // 8 channels at a time keeps the live registers low
               const int ch = c0 + 8 * h;
@@ -521,7 +606,7 @@ conv_tile_kernel(const TileParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 }  // namespace itg

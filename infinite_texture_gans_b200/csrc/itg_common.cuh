@@ -40,6 +40,28 @@ template <> struct __align__(16) Vec8<__half> { __half v[8]; };
 template <> struct __align__(16) Vec8<__nv_bfloat16> { __nv_bfloat16 v[8]; };
 template <> struct __align__(16) Vec8<float> { float v[8]; };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.256): one 16-channel pixel of a 16-bit grid tensor per instruction
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7]), "l"(p)
+               : "memory");
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<float>(float a, float) { return __float_as_uint(a); }   // (unused: 16-bit tensors only)
+
 template <typename T>
 __device__ __forceinline__ void load8(const T* __restrict__ p, float (&f)[8]) {
   if constexpr (sizeof(T) == 2) {
