@@ -236,7 +236,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);            // one arrival per epilogue warp of the group
+      mbar_init(bar_tempty + 8 * i, 8);            // one arrival per epilogue warp (both groups work on every item)
     }
     fence_barrier_init();
   }
@@ -346,26 +346,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       __syncwarp();
     }
     if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = dacc[0]; p.dbg[3] = dacc[1]; p.dbg[4] = dacc[2]; }
-  } else if (warp >= 4) {                                              // ---- epilogue: group g drains every second item ----
-    const int g = (warp - 4) >> 2;
+  } else if (warp >= 4) {                                              // ---- epilogue: both groups drain every item, group g takes the
+    const int g = (warp - 4) >> 2;                                     //      16-column chunks c = g (mod 2): half the latency per item ----
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    int li = g;
+    int li = 0;
     unsigned long long dacc[2] = {0, 0};
     long long tl = p.dbg ? clock64() : 0;
-    for (int w = w_first + g * w_stride; w < w_limit; w += 2 * w_stride, li += 2) {
+    for (int w = w_first; w < w_limit; w += w_stride, ++li) {
       int tile, phase, n0;
       decode(w, tile, phase, n0);
+      const int b = li & 1;
       const uint32_t bph = (uint32_t)(li >> 1) & 1u;
       const int y = (tile / p.tiles_x) * th + (row >> p.tw_log2), x = (tile % p.tiles_x) * tw + (row & (tw - 1));
       const bool valid = (y < p.m_h) && (x < p.m_w);
       int oy = y, ox = x;
       if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
-      if (lane == 0) mbar_wait(bar_tfull + 8 * g, bph);
+      if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);
       __syncwarp();
       ITG_UACC(0, tl);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)g * buf_cols;
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)b * buf_cols;
       // interior tile (all pixels valid, none on the image border) with a specialised epilogue: addresses are formed once
       // per pixel and no frame logic runs; border tiles and the generic / SSM / image epilogues take the general path
       const int ty0 = (tile / p.tiles_x) * th, tx0 = (tile % p.tiles_x) * tw;
@@ -374,7 +375,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const EpiParams& ep = p.ep;
         const size_t off = grid_off(oy, ox, ep.out_w, ep.out_c, 0);
         const T* rp = (F & EF_RES) ? reinterpret_cast<const T*>(ep.res) + grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, 0) : nullptr;
-        for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
+        for (int c0 = 16 * g; c0 < p.n_blk; c0 += 32) {
           float v[16];
           tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
@@ -412,7 +413,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       } else
-      for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
+      for (int c0 = 16 * g; c0 < p.n_blk; c0 += 32) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
         if (valid) {
@@ -429,7 +430,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(bar_tempty + 8 * g);
+      if (lane == 0) mbar_arrive_cta(bar_tempty + 8 * b);
       ITG_UACC(1, tl);
     }
     if (p.dbg && blockIdx.x == 0 && ew == 0 && lane == 0) { p.dbg[5 + 2 * g] = dacc[0]; p.dbg[6 + 2 * g] = dacc[1]; }
