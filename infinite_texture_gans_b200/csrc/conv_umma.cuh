@@ -201,7 +201,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // between items, and with two TMEM accumulator buffers so that the epilogue of item i (two groups of four warps,
 // alternating items) overlaps the TMA loads and MMAs of item i+1.
 #define ITG_UACC(slot, tvar) do { if (p.dbg) { const long long now_ = clock64(); dacc[slot] += (unsigned long long)(now_ - tvar); tvar = now_; } } while (0)
-constexpr int UMMA_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..7 / 8..11 epilogue groups
+#ifndef ITG_UMMA_EPI_GROUPS
+#define ITG_UMMA_EPI_GROUPS 4
+#endif
+constexpr int UMMA_EPI_GROUPS = ITG_UMMA_EPI_GROUPS;      // groups of four epilogue warps; group g drains the 16-column chunks c = g (mod G) of EVERY item
+constexpr int UMMA_THREADS = 32 * (4 + 4 * UMMA_EPI_GROUPS);     // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue
 constexpr int UMMA_BAR_BYTES = 1024;
 constexpr int UMMA_MAX_STAGES = 8;
 
@@ -236,7 +240,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 8);            // one arrival per epilogue warp (both groups work on every item)
+      mbar_init(bar_tempty + 8 * i, 4 * UMMA_EPI_GROUPS);   // one arrival per epilogue warp (all groups work on every item)
     }
     fence_barrier_init();
   }
@@ -362,20 +366,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const bool valid = (y < p.m_h) && (x < p.m_w);
       int oy = y, ox = x;
       if (p.mode == ITG_UPCONV) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
+      // interior tile (all pixels valid, none on the image border) with a specialised epilogue: addresses are formed once
+      // per pixel and no frame logic runs; border tiles and the generic / SSM / image epilogues take the general path
+      const int ty0 = (tile / p.tiles_x) * th, tx0 = (tile % p.tiles_x) * tw;
+      const bool interior = (F & (EF_GENERIC | EF_IMG)) == 0 && ty0 > 0 && tx0 > 0 && ty0 + th < p.m_h && tx0 + tw < p.m_w;
+      constexpr int CSTEP = 16 * UMMA_EPI_GROUPS;
+      // the residual does not depend on the accumulators: the chunk's 32 bytes are fetched one chunk ahead, the first
+      // one before sleeping on the MMA barrier
+      const T* rp = nullptr;
+      uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
+      if ((F & EF_RES) != 0 && interior) {
+        rp = reinterpret_cast<const T*>(p.ep.res) + grid_off(oy >> p.ep.res_shift, ox >> p.ep.res_shift, p.ep.res_w, p.ep.res_c, 0);
+        const int ch = n0 + 16 * g;
+        if (16 * g < p.n_blk && ch < p.ep.out_c) {
+          rn0 = *reinterpret_cast<const uint4*>(rp + ch);
+          if (ch + 8 < p.ep.out_c) rn1 = *reinterpret_cast<const uint4*>(rp + ch + 8);
+        }
+      }
       if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);
       __syncwarp();
       ITG_UACC(0, tl);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)b * buf_cols;
-      // interior tile (all pixels valid, none on the image border) with a specialised epilogue: addresses are formed once
-      // per pixel and no frame logic runs; border tiles and the generic / SSM / image epilogues take the general path
-      const int ty0 = (tile / p.tiles_x) * th, tx0 = (tile % p.tiles_x) * tw;
-      const bool interior = (F & (EF_GENERIC | EF_IMG)) == 0 && ty0 > 0 && tx0 > 0 && ty0 + th < p.m_h && tx0 + tw < p.m_w;
       if (interior) {
         const EpiParams& ep = p.ep;
         const size_t off = grid_off(oy, ox, ep.out_w, ep.out_c, 0);
-        const T* rp = (F & EF_RES) ? reinterpret_cast<const T*>(ep.res) + grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, 0) : nullptr;
-        for (int c0 = 16 * g; c0 < p.n_blk; c0 += 32) {
+        for (int c0 = 16 * g; c0 < p.n_blk; c0 += CSTEP) {
+          uint4 rc[2] = {rn0, rn1};
+          if (F & EF_RES) {
+            const int chn = n0 + c0 + CSTEP;
+            if (c0 + CSTEP < p.n_blk && chn < ep.out_c) {
+              rn0 = *reinterpret_cast<const uint4*>(rp + chn);
+              if (chn + 8 < ep.out_c) rn1 = *reinterpret_cast<const uint4*>(rp + chn + 8);
+            }
+          }
           float v[16];
           tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
@@ -387,10 +411,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             x8[0] = v[8 * h] + ba.x; x8[1] = v[8 * h + 1] + ba.y; x8[2] = v[8 * h + 2] + ba.z; x8[3] = v[8 * h + 3] + ba.w;
             x8[4] = v[8 * h + 4] + bb.x; x8[5] = v[8 * h + 5] + bb.y; x8[6] = v[8 * h + 6] + bb.z; x8[7] = v[8 * h + 7] + bb.w;
             if (F & EF_RES) {
-              float r8[8];
-              load8(rp + ch, r8);
+              const Vec8<T> t0 = *reinterpret_cast<const Vec8<T>*>(&rc[h]);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x8[i] += r8[i];
+              for (int i = 0; i < 8; ++i) x8[i] += Op<T>::to_f(t0.v[i]);
             }
             if (F & EF_RAW) store8(reinterpret_cast<T*>(ep.out_raw) + off + ch, x8);
             if (F & EF_ACT) {
@@ -413,7 +436,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       } else
-      for (int c0 = 16 * g; c0 < p.n_blk; c0 += 32) {
+      for (int c0 = 16 * g; c0 < p.n_blk; c0 += CSTEP) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
         if (valid) {
