@@ -26,16 +26,16 @@ constexpr int TILE_W = 8, TILE_H = 16;                       // output tile = 12
 constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;      // input neighbourhood
 constexpr int HALO_PX = HALO_W * HALO_H;                     // 180
 constexpr int PLANE_BYTES = HALO_PX * 16;                    // one 8-channel plane of the halo tile: 2880 B
-#ifndef ITG_TILE_EPI_GROUPS
-#define ITG_TILE_EPI_GROUPS 4
-#endif
-// Warp roles: warps 0..NM-1 issue MMAs (one per scheduler), warps 4..4+4G-1 are G epilogue groups of four warps (TMEM lane
-// quarter = warp % 4), the three producers are the remaining warps below 4 plus the warps after the epilogue groups.
-// MMA warp m and epilogue group m work on the same tiles (it = m mod NM) and so form independent pipelines.
-constexpr int TILE_EPI_GROUPS = ITG_TILE_EPI_GROUPS;
-constexpr int TILE_MMA_WARPS = TILE_EPI_GROUPS;
-constexpr int TILE_PWARPS = 3;              // producer warps: each loads every third tile on its own
-constexpr int TILE_WARPS = 4 + 4 * TILE_EPI_GROUPS + (TILE_PWARPS - (4 - TILE_MMA_WARPS));
+// Warp roles: the CTA runs TILE_PIPES independent pipelines.  Pipeline m = producer warp (4 + 4 * PIPES + m), MMA warp m
+// (one per scheduler) and epilogue group m (warps 4 + 4m .. 7 + 4m; TMEM lane quarter = warp % 4); it owns the tiles
+// it = m (mod pipes) of this CTA, a private ring of input stages and private TMEM accumulator buffers.  Every mbarrier
+// therefore has exactly one arriving and one waiting party that walk its phases in order -- parity waits are only
+// safe under that condition (a warp that shares a barrier with a faster sibling can alias a phase; an ncu
+// instrumentation pass found exactly that in an earlier round-robin version).
+constexpr int TILE_PIPES = 4;
+constexpr int TILE_EPI_GROUPS = TILE_PIPES;
+constexpr int TILE_MMA_WARPS = TILE_PIPES;
+constexpr int TILE_WARPS = 4 + 4 * TILE_PIPES + TILE_PIPES;
 constexpr int TILE_THREADS = 32 * TILE_WARPS;
 constexpr int TILE_HDR_BYTES = 2048;       // barriers + per-channel epilogue vectors (bias | scale | shift | scale*bias+shift)
 constexpr int TILE_MAX_STAGES = 24;
@@ -55,8 +55,9 @@ struct TileParams {
   int taps_w;              // taps in the weight tensor: 9 | 1 | 16
   int w_bytes;             // bytes of the shared-memory weight image
   int stage_bytes;         // bytes of one input stage (kg planes)
-  int stages, ahead;       // input ring depth; tiles a producer WARP keeps in flight before publishing (0..2)
-  int nbuf;                // TMEM accumulator buffers (2 or 4)
+  int stages, ahead;       // input stages in total (= pipes * ring); tiles a producer keeps in flight before publishing (< ring)
+  int pipes, ring;         // active pipelines (<= TILE_PIPES, <= nbuf) and input stages per pipeline
+  int nbuf;                // TMEM accumulator buffers (power of two, multiple of pipes)
   uint32_t tmem_cols;
   uint32_t idesc;
   const void* w;
@@ -183,8 +184,8 @@ conv_tile_kernel(const TileParams p) {
   // Loop bookkeeping without integer division: ring positions advance by a fixed step, tile coordinates by a
   // precomputed (dy, dx) with carry.  mbarrier waits are done by lane 0 only (a 32-lane try_wait on one barrier
   // measured ~300 cycles even when already complete) followed by __syncwarp.
-  if ((warp >= TILE_MMA_WARPS && warp < 4) || warp >= 4 + 4 * TILE_EPI_GROUPS) {  // ---- producers ----
-    const int pw = warp < 4 ? warp - TILE_MMA_WARPS : (4 - TILE_MMA_WARPS) + warp - (4 + 4 * TILE_EPI_GROUPS);   // producer 0..2 loads tiles it = 3k + pw, all 32 lanes on one tile
+  if (warp >= 4 + 4 * TILE_EPI_GROUPS) {                                        // ---- producers: one warp per pipeline, all 32 lanes on one tile ----
+    const int pw = warp - (4 + 4 * TILE_EPI_GROUPS);
     const int kg_log2 = 31 - __clz(p.kg);
     const int cg_total = p.in_c >> 3;
     const T* in = reinterpret_cast<const T*>(p.in);
@@ -196,13 +197,14 @@ conv_tile_kernel(const TileParams p) {
     // per-lane offsets of its halo pixels (<= 45 at kg = 2 ... 12 at kg = 8): computed on the fly, two multiplies each
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
-    const int step = TILE_PWARPS * (int)gridDim.x;
+    const int step = p.pipes * (int)gridDim.x;
     const int sdy = step / p.tiles_x, sdx = step - sdy * p.tiles_x;
-    int tile = blockIdx.x + pw * (int)gridDim.x;
+    int tile = pw < p.pipes ? blockIdx.x + pw * (int)gridDim.x : p.ntiles;
     int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-    int s = pw % p.stages;                 // stage of tile it
-    uint32_t ph = (uint32_t)(pw / p.stages) & 1u;
-    int s_pub = s;                         // stage of the tile to publish (ahead iterations behind)
+    const int s0 = pw * p.ring;            // first stage of this pipeline's private ring
+    int s = s0;                            // stage of tile k
+    uint32_t ph = 0;
+    int s_pub = s0;                        // stage of the tile to publish (ahead iterations behind)
     int k = 0;
     for (; tile < p.ntiles; tile += step, ++k) {
       const int y0 = ty * TILE_H, x0 = tx * TILE_W;                            // halo origin in buffer pixels
@@ -232,17 +234,17 @@ conv_tile_kernel(const TileParams p) {
         ITG_ACC(2, tl);
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s_pub);
-        s_pub += TILE_PWARPS; if (s_pub >= p.stages) s_pub -= p.stages;
+        if (++s_pub == s0 + p.ring) s_pub = s0;
         ITG_ACC(3, tl);
       }
-      s += TILE_PWARPS; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+      if (++s == s0 + p.ring) { s = s0; ph ^= 1u; }
       tx += sdx; ty += sdy; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
     }
     cp_async_wait_dyn(0);
     fence_proxy_async();
     for (int q = (k > p.ahead ? k - p.ahead : 0); q < k; ++q) {
       mbar_arrive(bar_full + 8 * s_pub);
-      s_pub += TILE_PWARPS; if (s_pub >= p.stages) s_pub -= p.stages;
+      if (++s_pub == s0 + p.ring) s_pub = s0;
     }
     if (p.dbg && pw == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_acc[i];
   } else if (warp < TILE_MMA_WARPS) {                                          // ---- MMA warps (uniform; one lane issues), tiles it = mw (mod NM) ----
@@ -252,10 +254,10 @@ conv_tile_kernel(const TileParams p) {
     const int ksteps = p.kg >> 1;
     const uint32_t w16 = w_smem >> 4, n16 = (uint32_t)p.n;                     // weight image: 16 B per (k-group, n)
     const int nbuf_log2 = 31 - __clz(p.nbuf);
-    // an accumulator buffer must belong to ONE MMA warp / epilogue group (parity waits), so no more of them than buffers
-    const int nm = p.nbuf < TILE_MMA_WARPS ? p.nbuf : TILE_MMA_WARPS;
-    int s = mw % p.stages;
-    uint32_t ph = (uint32_t)(mw / p.stages) & 1u;
+    const int nm = p.pipes;
+    const int s0 = mw * p.ring;
+    int s = s0;
+    uint32_t ph = 0;
     int it = mw;
     for (int tile = mw < nm ? blockIdx.x + mw * (int)gridDim.x : p.ntiles; tile < p.ntiles; tile += nm * gridDim.x, it += nm) {
       const int b = it & (p.nbuf - 1);
@@ -280,7 +282,7 @@ conv_tile_kernel(const TileParams p) {
       }
       __syncwarp();
       ITG_ACC(2, tl);
-      s += nm; if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+      if (++s == s0 + p.ring) { s = s0; ph ^= 1u; }
     }
     if (p.dbg && lane == 0 && mw == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i];
   } else if (warp >= 4 && warp < 4 + 4 * TILE_EPI_GROUPS) {                    // ---- epilogue ----
@@ -295,7 +297,7 @@ conv_tile_kernel(const TileParams p) {
     // instructions per pixel; everything else takes the general path below.
     constexpr bool FASTF = (F & EF_GENERIC) == 0;
     const bool fast = FASTF && ((F & EF_IMG) != 0 || ep.out_c <= p.n);
-    const bool n16 = p.n == 16 && TILE_EPI_GROUPS <= 2;    // (more groups = fewer registers per thread: vectors stay in shared memory)
+    const bool n16 = false;      // (register-resident vector variant for 16-column layers: needs > 88 registers, disabled with four pipelines)
     float rb[16], rs[16], rt[16];                        // n == 16: the vectors stay in registers
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -311,8 +313,7 @@ conv_tile_kernel(const TileParams p) {
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
     const int nbuf_log2 = 31 - __clz(p.nbuf);
-    // a group may wait at most one barrier phase ahead (parity waits), so no more groups than accumulator buffers
-    const int ngroups = p.nbuf < TILE_EPI_GROUPS ? p.nbuf : TILE_EPI_GROUPS;
+    const int ngroups = p.pipes;
     const int step = ngroups * (int)gridDim.x;
     const int sdy = step / p.tiles_x, sdx = step - sdy * p.tiles_x;
     int tile = g < ngroups ? blockIdx.x + g * (int)gridDim.x : p.ntiles;

@@ -63,11 +63,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a broken pipeline traps (the launch fails) instead of hanging the device.
+#ifndef ITG_MBAR_TIMEOUT_CYCLES
+#define ITG_MBAR_TIMEOUT_CYCLES 4000000000LL      // ~2 s
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  // bounded: a broken pipeline traps instead of hanging the GPU.  Both a cycle budget and a poll budget must be exhausted:
+  // a profiler that freezes the SM for seconds (ncu PM-sampling passes) advances the clock but not the polls.
   const long long t0 = clock64();
+  unsigned polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++polls > (1u << 20) && clock64() - t0 > ITG_MBAR_TIMEOUT_CYCLES) {
       printf("itg: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, bar, parity);
       __trap();

@@ -354,20 +354,15 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   p.stage_bytes = p.kg * itg::PLANE_BYTES;
   int stages = (TILE_SMEM_BUDGET - itg::TILE_HDR_BYTES - 128 - p.w_bytes) / p.stage_bytes;
   if (stages > itg::TILE_MAX_STAGES) stages = itg::TILE_MAX_STAGES;
-  static const int env_stages = getenv("ITG_TILE_STAGES") ? atoi(getenv("ITG_TILE_STAGES")) : 0;      // developer sweeps
-  static const int env_ahead = getenv("ITG_TILE_AHEAD") ? atoi(getenv("ITG_TILE_AHEAD")) : -1;
-  static const int env_nbuf = getenv("ITG_TILE_NBUF") ? atoi(getenv("ITG_TILE_NBUF")) : 0;
-  if (env_stages >= 4 && stages > env_stages) stages = env_stages;
-  p.stages = stages;
-  p.ahead = (stages - 2) / 3 - 1;         // per producer warp: 3 warps x (ahead + 1) tiles in flight leave two free stages
-  if (p.ahead < 0) p.ahead = 0;
-  const int ahead_cap = env_ahead >= 0 ? env_ahead : 2;
-  if (p.ahead > ahead_cap) p.ahead = ahead_cap;
-  if (p.ahead > 7) p.ahead = 7;
   const int nphase = d.mode == ITG_UPCONV ? 4 : 1;
   p.nbuf = 2;                              // accumulator ring: as deep as TMEM allows (power of two, <= 8)
-  const int nbuf_cap = (env_nbuf == 2 || env_nbuf == 4 || env_nbuf == 8) ? env_nbuf : itg::TILE_MAX_NBUF;
-  while (p.nbuf * 2 <= nbuf_cap && p.nbuf * 2 * nphase * p.n <= 512) p.nbuf *= 2;
+  while (p.nbuf * 2 <= itg::TILE_MAX_NBUF && p.nbuf * 2 * nphase * p.n <= 512) p.nbuf *= 2;
+  p.pipes = p.nbuf < itg::TILE_PIPES ? p.nbuf : itg::TILE_PIPES;     // each pipeline needs an accumulator buffer of its own
+  if (stages < p.pipes) p.pipes = stages >= 2 ? 2 : 1;              // ... and at least one input stage
+  p.ring = stages / p.pipes;
+  stages = p.ring * p.pipes;
+  p.stages = stages;
+  p.ahead = p.ring - 1 < 2 ? p.ring - 1 : 2;      // tiles a producer keeps in flight before publishing the oldest
   uint32_t cols = 32;
   while ((int)cols < p.nbuf * nphase * p.n) cols <<= 1;
   p.tmem_cols = cols;

@@ -83,6 +83,11 @@ CONV_CASES = [
     ("up", 130, 50, 26, 13, dict(act=True, border=L.BORDER_CONSTANT)),
     ("1x1", 70, 90, 52, 26, dict(raw=True)),
     ("3x3", 260, 136, 13, 3, dict(img=L.IMG_PATCHES, patch=4)),
+    # halo-tile kernel corner cases: 4 x 48 accumulator columns per tile (only two TMEM buffers -> two MMA warps / epilogue
+    # groups active), and 32-channel tensors with a residual (256-bit epilogue loads / stores, two chunks per pixel)
+    ("up", 40, 56, 64, 48, dict(act=True, border=L.BORDER_REPLICATE)),
+    ("3x3", 90, 70, 32, 32, dict(raw=True, act=True, res=0, border=L.BORDER_REPLICATE)),
+    ("3x3", 50, 38, 32, 32, dict(raw=True, res=1, border=L.BORDER_NONE)),
 ]
 
 
