@@ -325,7 +325,8 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
-constexpr int TILE_SMEM_BUDGET = 200 * 1024;
+static int tile_smem_budget() { static const int v = getenv("ITG_TILE_SMEM_KB") ? atoi(getenv("ITG_TILE_SMEM_KB")) * 1024 : 224 * 1024; return v; }
+#define TILE_SMEM_BUDGET tile_smem_budget()
 
 // thin layers: K <= 64 per tap, N <= 64 -> persistent halo-tile kernel (conv_tile.cuh)
 bool tile_eligible(const itg_conv_desc& d) {
@@ -358,6 +359,10 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   p.nbuf = 2;                              // accumulator ring: as deep as TMEM allows (power of two, <= 8)
   while (p.nbuf * 2 <= itg::TILE_MAX_NBUF && p.nbuf * 2 * nphase * p.n <= 512) p.nbuf *= 2;
   p.pipes = p.nbuf < itg::TILE_PIPES ? p.nbuf : itg::TILE_PIPES;     // each pipeline needs an accumulator buffer of its own
+  static const int env_pipes = getenv("ITG_TILE_PIPES") ? atoi(getenv("ITG_TILE_PIPES")) : 0;          // developer sweeps
+  static const int env_minring = getenv("ITG_TILE_MINRING") ? atoi(getenv("ITG_TILE_MINRING")) : 1;
+  if ((env_pipes == 1 || env_pipes == 2) && p.pipes > env_pipes) p.pipes = env_pipes;
+  while (p.pipes > 1 && stages / p.pipes < env_minring) p.pipes >>= 1;
   if (stages < p.pipes) p.pipes = stages >= 2 ? 2 : 1;              // ... and at least one input stage
   p.ring = stages / p.pipes;
   stages = p.ring * p.pipes;
