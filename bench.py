@@ -201,9 +201,29 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 prints exactly one JSON line on stdout: NCCL's version banner (written to fd 1 at communicator creation) goes to stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+        # pinned host buffers should live on the GPU's own NUMA node (8 ranks copying 29 MB images per step share the host's memory system)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(local)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+            except Exception:                                        # noqa: BLE001
+                h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+        except Exception as e:                                       # noqa: BLE001  (affinity is an optimisation only)
+            print(f"[bench] rank {rank}: could not set CPU affinity ({type(e).__name__}: {e})", file=sys.stderr)
 
     cfg = GenConfig(**kw)
     P = cfg.patch_px

@@ -31,6 +31,8 @@ struct UmmaParams {
   unsigned long long* dbg;  // optional per-role cycle counters of CTA 0 (ITG_TILE_DBG=1)
   int kc, nchunks, ksteps_last;
   int stages;
+  int teams, groups;     // active epilogue groups (2 or 4) in 1 or 2 teams.  teams = 1: every active group drains every work item (latency:
+                         // few items per CTA); teams = 2: team t drains the items li = t (mod 2), i.e. accumulator buffer t (throughput)
   int a_bytes, b_bytes;  // per-stage operand bytes (also the TMA transaction size)
   int a_stride, b_stride;  // 1024-aligned strides inside a stage
   uint32_t sbo_enc;      // (8 * swizzle bytes) >> 4
@@ -246,7 +248,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4 * UMMA_EPI_GROUPS);   // one arrival per epilogue warp (all groups work on every item)
+      mbar_init(bar_tempty + 8 * i, 4 * p.groups / p.teams);   // one arrival per epilogue warp of the team that drains this buffer
     }
     fence_barrier_init();
   }
@@ -360,10 +362,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int g = (warp - 4) >> 2;                                     //      16-column chunks c = g (mod 2): half the latency per item ----
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    int li = 0;
+    // team t = groups of which it consists drain the items li = t (mod teams) (accumulator buffer li & 1); inside a team
+    // group gi of gpt takes the 16-column chunks c = gi (mod gpt)
+    const int gpt = p.groups / p.teams;
+    const int team = g / gpt, gi = g - team * gpt;
+    int li = team;
     unsigned long long dacc[2] = {0, 0};
     long long tl = p.dbg ? clock64() : 0;
-    for (int w = w_first; w < w_limit; w += w_stride, ++li) {
+    const int cstep = 16 * gpt;
+    for (int w = g < p.groups ? w_first + team * w_stride : w_limit; w < w_limit; w += p.teams * w_stride, li += p.teams) {
       int tile, phase, n0;
       decode(w, tile, phase, n0);
       const int b = li & 1;
@@ -376,15 +383,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // per pixel and no frame logic runs; border tiles and the generic / SSM / image epilogues take the general path
       const int ty0 = (tile / p.tiles_x) * th, tx0 = (tile % p.tiles_x) * tw;
       const bool interior = (F & (EF_GENERIC | EF_IMG)) == 0 && ty0 > 0 && tx0 > 0 && ty0 + th < p.m_h && tx0 + tw < p.m_w;
-      constexpr int CSTEP = 16 * UMMA_EPI_GROUPS;
       // the residual does not depend on the accumulators: the chunk's 32 bytes are fetched one chunk ahead, the first
       // one before sleeping on the MMA barrier
       const T* rp = nullptr;
       uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
       if ((F & EF_RES) != 0 && interior) {
         rp = reinterpret_cast<const T*>(p.ep.res) + grid_off(oy >> p.ep.res_shift, ox >> p.ep.res_shift, p.ep.res_w, p.ep.res_c, 0);
-        const int ch = n0 + 16 * g;
-        if (16 * g < p.n_blk && ch < p.ep.out_c) {
+        const int ch = n0 + 16 * gi;
+        if (16 * gi < p.n_blk && ch < p.ep.out_c) {
           rn0 = *reinterpret_cast<const uint4*>(rp + ch);
           if (ch + 8 < p.ep.out_c) rn1 = *reinterpret_cast<const uint4*>(rp + ch + 8);
         }
@@ -397,11 +403,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (interior) {
         const EpiParams& ep = p.ep;
         const size_t off = grid_off(oy, ox, ep.out_w, ep.out_c, 0);
-        for (int c0 = 16 * g; c0 < p.n_blk; c0 += CSTEP) {
+        for (int c0 = 16 * gi; c0 < p.n_blk; c0 += cstep) {
           uint4 rc[2] = {rn0, rn1};
           if (F & EF_RES) {
-            const int chn = n0 + c0 + CSTEP;
-            if (c0 + CSTEP < p.n_blk && chn < ep.out_c) {
+            const int chn = n0 + c0 + cstep;
+            if (c0 + cstep < p.n_blk && chn < ep.out_c) {
               rn0 = *reinterpret_cast<const uint4*>(rp + chn);
               if (chn + 8 < ep.out_c) rn1 = *reinterpret_cast<const uint4*>(rp + chn + 8);
             }
@@ -442,7 +448,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       } else
-      for (int c0 = 16 * g; c0 < p.n_blk; c0 += CSTEP) {
+      for (int c0 = 16 * gi; c0 < p.n_blk; c0 += cstep) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
         if (valid) {

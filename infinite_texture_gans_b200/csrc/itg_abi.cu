@@ -238,6 +238,9 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   if (stages > total_iters) stages = total_iters;
   if (stages < 1) return fail(ITG_ERR_UNSUPPORTED, "conv: stage of %d bytes does not fit shared memory", stage_bytes);
   p.stages = stages;
+  // few items per CTA: an item's epilogue is exposed, drain it with every warp; many: two teams alternate items
+  static const int env_teams = getenv("ITG_UMMA_TEAMS") ? atoi(getenv("ITG_UMMA_TEAMS")) : 0;          // developer sweeps
+  p.teams = (env_teams == 1 || env_teams == 2) ? env_teams : 0;
   uint32_t cols = 32;
   while ((int)cols < 2 * p.n_blk) cols <<= 1;              // two accumulator buffers
   p.tmem_cols = cols;
@@ -278,6 +281,12 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
     if (nclusters > p.nitems) nclusters = p.nitems;
     grid = nclusters * p.cluster;
   }
+  // few items per CTA: an item's epilogue is exposed -> all four groups drain every item together; many items: two groups
+  // alternate items (fewer warps competing with the MMA warp for issue slots: 4-8 % faster main loop on large grids)
+  const bool many = (p.cluster > 1 ? p.nitems * p.cluster : p.nwork) > 2 * grid;
+  if (p.teams == 0) p.teams = many ? 2 : 1;
+  static const int env_groups = getenv("ITG_UMMA_GROUPS") ? atoi(getenv("ITG_UMMA_GROUPS")) : 0;
+  p.groups = (env_groups == 2 || env_groups == 4) ? env_groups : (many ? 2 : itg::UMMA_EPI_GROUPS);
   int flags = itg::EF_GENERIC;
   if (!d.mod_x && !d.out_f32 && d.res_kind != ITG_RES_F32) {
     if (d.out_img) flags = itg::EF_IMG;
