@@ -289,30 +289,16 @@ conv_tile_kernel(const TileParams p) {
     }
     if (p.dbg && lane == 0 && mw == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + 4 + i] = dbg_acc[i];
   } else if (warp >= 4 && warp < 4 + 4 * TILE_EPI_GROUPS) {                    // ---- epilogue ----
-    // groups of four warps; group g drains every TILE_EPI_GROUPS-th tile of this CTA (accumulator buffer it % nbuf)
+    // group g drains the tiles of pipeline g (accumulator buffer it % nbuf)
     const int g = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
     const EpiParams& ep = p.ep;
     const uint32_t vec_smem = sbase + TILE_VEC_OFF;     // bias | scale | shift copies (see load_vec8)
-    // Fast path (n == 16, tile not touching the image border, specialised epilogue): bias / BN scale / folded shift of the
-    // 16 channels live in registers, addresses are formed once per pixel, no frame logic.  ~100 instead of ~250
-    // instructions per pixel; everything else takes the general path below.
+    // Fast path (tile not touching the image border, specialised epilogue): addresses are formed once per pixel, the
+    // per-channel vectors come from shared memory, no frame logic; everything else takes the general path below.
     constexpr bool FASTF = (F & EF_GENERIC) == 0;
     const bool fast = FASTF && ((F & EF_IMG) != 0 || ep.out_c <= p.n);
-    const bool n16 = false;      // (register-resident vector variant for 16-column layers: needs > 88 registers, disabled with four pipelines)
-    float rb[16], rs[16], rt[16];                        // n == 16: the vectors stay in registers
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      rb[i] = (fast && n16) ? vec[i] : 0.f;
-      rs[i] = (fast && n16) ? vec[64 + i] : 1.f;
-      rt[i] = (fast && n16) ? vec[192 + i] : 0.f;
-    }
-    unsigned long long rb2[8], rs2[8], rt2[8];           // the same, packed two channels wide for FADD2 / FFMA2
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { rb2[i] = pk2(rb[2 * i], rb[2 * i + 1]); rs2[i] = pk2(rs[2 * i], rs[2 * i + 1]); rt2[i] = pk2(rt[2 * i], rt[2 * i + 1]); }
-    const bool leak01 = ep.leak >= 0.f && ep.leak <= 1.f;     // leaky(x) == max(x, leak * x)
-    const unsigned long long leak2 = pk2(ep.leak, ep.leak);
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
     const int nbuf_log2 = 31 - __clz(p.nbuf);
@@ -326,35 +312,15 @@ conv_tile_kernel(const TileParams p) {
     // pixels of 16 k channels are 32-byte aligned: 256-bit loads / stores, one per 16 channels
     const bool wide = sizeof(T) == 2 && (ep.out_c & 15) == 0 && (!(F & EF_RES) || (ep.res_c & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(ep.out_raw) | reinterpret_cast<uintptr_t>(ep.out_act) | reinterpret_cast<uintptr_t>(ep.res)) & 31) == 0;
-    const bool pipe_res = PRE && n16;
-    uint4 nxt[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    if (pipe_res && tile < p.ntiles) {
-      const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
-      if (y < p.m_h && x < p.m_w) {
-        const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(y >> ep.res_shift, x >> ep.res_shift, ep.res_w, ep.res_c, 0);
-        nxt[0] = *reinterpret_cast<const uint4*>(rp);
-        if (ep.out_c > 8) nxt[1] = *reinterpret_cast<const uint4*>(rp + 8);
-      }
-    }
     for (; tile < p.ntiles; tile += step, it += ngroups) {
       const int b = it & (p.nbuf - 1);
       const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
       const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
       const bool valid = (y < p.m_h) && (x < p.m_w);
-      // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier -- and, for the
-      // 16-channel layers, one whole tile ahead (nxt), so that their latency never sits between two tiles
+      // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier (fetching them a
+      // whole tile ahead was measured slower: the extra live registers spill under the 80-register cap)
       uint4 pre[8];
-      if (PRE && pipe_res) {
-        pre[0] = nxt[0]; pre[1] = nxt[1];
-        int nty = ty + sdy, ntx = tx + sdx;
-        if (ntx >= p.tiles_x) { ntx -= p.tiles_x; ++nty; }
-        const int ny = nty * TILE_H + (row >> 3), nx = ntx * TILE_W + (row & 7);
-        if (tile + step < p.ntiles && ny < p.m_h && nx < p.m_w) {
-          const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(ny >> ep.res_shift, nx >> ep.res_shift, ep.res_w, ep.res_c, 0);
-          nxt[0] = *reinterpret_cast<const uint4*>(rp);
-          if (ep.out_c > 8) nxt[1] = *reinterpret_cast<const uint4*>(rp + 8);
-        }
-      } else if (PRE && valid) {
+      if (PRE && valid) {
         const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(y >> ep.res_shift, x >> ep.res_shift, ep.res_w, ep.res_c, 0);
         if (wide) {                                                              // 16 channels (32 B) per load
 #pragma unroll
@@ -372,86 +338,6 @@ conv_tile_kernel(const TileParams p) {
       tc_fence_after();
       // interior tile: every pixel valid and none of its outputs on the image border (no frame writes needed)
       const bool interior = fast && ty > 0 && tx > 0 && (ty + 1) * TILE_H < p.m_h && (tx + 1) * TILE_W < p.m_w;
-      if (interior && n16) {                                                     // 16 channels: vectors in registers, one pass
-#pragma unroll
-        for (int q = 0; q < NPHASE; ++q) {
-          int oy = y, ox = x;
-          if (MODE == ITG_UPCONV) { oy = 2 * y + (q >> 1); ox = 2 * x + (q & 1); }
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * NPHASE + q) * 16), v);
-          if (F & EF_IMG) {                                                      // final conv: tanh -> planar fp32 image
-            if (ep.img_layout == ITG_IMG_MERGED) {
-              float* o = ep.out_img + (size_t)oy * ep.out_w + ox;
-              const size_t plane = (size_t)ep.out_h * ep.out_w;
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                if (c < ep.img_c) o[c * plane] = tanh_fast(v[c] + rb[c]);
-            } else {
-              float a[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] = v[i];
-              epilogue8<T, F>(ep, oy, ox, 0, a, nullptr, vec_smem);
-            }
-            continue;
-          }
-          unsigned long long v2[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v2[i] = pk2(v[2 * i], v[2 * i + 1]);
-          if (F & EF_RES) {
-            if (PRE) {
-              const __half2* h0 = reinterpret_cast<const __half2*>(&pre[0]);
-              const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&pre[0]);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {                                    // pre[0], pre[1] are adjacent: 8 channel pairs
-                float2 f;
-                if (sizeof(T) == 2 && std::is_same<T, __half>::value) f = __half22float2(h0[i]);
-                else f = __bfloat1622float2(b0[i]);
-                v2[i] = add2(v2[i], pk2(f.x, f.y));
-              }
-            } else {
-              const T* rp = reinterpret_cast<const T*>(ep.res) + grid_off(oy >> ep.res_shift, ox >> ep.res_shift, ep.res_w, ep.res_c, 0);
-              float r0[8], r1[8];
-              load8(rp, r0);
-              load8(rp + 8, r1);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { v2[i] = add2(v2[i], pk2(r0[2 * i], r0[2 * i + 1])); v2[4 + i] = add2(v2[4 + i], pk2(r1[2 * i], r1[2 * i + 1])); }
-            }
-          }
-          const size_t off = grid_off(oy, ox, ep.out_w, ep.out_c, 0);
-          if (F & EF_RAW) {
-            float w0[8], w1[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              unpk2(add2(v2[i], rb2[i]), w0[2 * i], w0[2 * i + 1]);
-              unpk2(add2(v2[4 + i], rb2[4 + i]), w1[2 * i], w1[2 * i + 1]);
-            }
-            T* o = reinterpret_cast<T*>(ep.out_raw) + off;
-            store8(o, w0);
-            if (ep.out_c > 8) store8(o + 8, w1);
-          }
-          if (F & EF_ACT) {
-            float w0[8], w1[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              unsigned long long y2 = fma2(rs2[i], v2[i], rt2[i]);
-              float ya, yb;
-              if (!ep.act_linear && leak01) {
-                float la, lb;
-                unpk2(mul2(y2, leak2), la, lb);
-                unpk2(y2, ya, yb);
-                ya = fmaxf(ya, la); yb = fmaxf(yb, lb);
-              } else {
-                unpk2(y2, ya, yb);
-                if (!ep.act_linear) { ya = act_fn(ya, ep.leak); yb = act_fn(yb, ep.leak); }
-              }
-              if (i < 4) { w0[2 * i] = ya; w0[2 * i + 1] = yb; } else { w1[2 * (i - 4)] = ya; w1[2 * (i - 4) + 1] = yb; }
-            }
-            T* o = reinterpret_cast<T*>(ep.out_act) + off;
-            store8(o, w0);
-            if (ep.out_c > 8) store8(o + 8, w1);
-          }
-        }
-      } else
       if (interior) {
 #pragma unroll
         for (int q = 0; q < NPHASE; ++q) {

@@ -151,30 +151,6 @@ __device__ __forceinline__ float tanh_fast(float x) {     // MUFU.TANH, abs erro
   return y;
 }
 
-// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2): same IEEE rounding per lane as the scalar instructions,
-// half the issue slots.  The thin-layer epilogues are issue-bound, so their per-channel math runs two channels wide.
-__device__ __forceinline__ unsigned long long pk2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpk2(unsigned long long r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 // Compile-time description of what an epilogue instance does, so that the thin-layer kernel (where the
 // per-pixel epilogue IS the cost) carries no dead branches.  EF_GENERIC = decide everything at run time.
 enum : int { EF_RES = 1, EF_RAW = 2, EF_ACT = 4, EF_IMG = 8, EF_GENERIC = 1 << 20 };
