@@ -374,6 +374,19 @@ def main():
                 pipe.wait(slot)
 
     pipe = itg.utils.HostOutputPipe(tuple(plan.out.shape), dev) if world > 1 else None
+    # (3) as (2) with the output stage of test_sample.py (img * 0.5 + 0.5 -> 8-bit, what save_image writes) done on the device:
+    # reported as e2e.u8_value, N = 1 only; the headline e2e stays the fp32 image the reference's sampler returns
+    e2e_u8 = None
+    if world == 1:
+        def run_stream_u8(n):
+            for _img in itg.utils.generate_textures(net, ((z_pin, maps_pin) for _ in range(n)), th * P, tw * P, graph=use_graph, out_format="uint8"):
+                pass
+        run_stream_u8(3)
+        barrier()
+        t0 = time.perf_counter()
+        run_stream_u8(args.steps)
+        barrier()
+        e2e_u8 = mp_step / ((time.perf_counter() - t0) / args.steps)
     run_stream(3)
     barrier()
     t0 = time.perf_counter()
@@ -437,7 +450,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "mode": "streaming public API (utils.generate_textures): per step H2D of the noise from pinned memory + D2H of the fp32 image into "
                                 "pinned memory, image k's D2H overlapped with pass k+1; wall clock over K steps incl. the last copy",
-                        "sync_value": e2e_sync_value, "sync_mode": "one blocking sample_from_gen_PatchByPatch_test call + D2H per step"},
+                        "sync_value": e2e_sync_value, "sync_mode": "one blocking sample_from_gen_PatchByPatch_test call + D2H per step",
+                        "u8_value": e2e_u8, "u8_mode": "as value, with test_sample.py's 8-bit output stage on the device (d2h = 1/4 of d2h_bytes_per_step)"},
                 "roofline": roof}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base

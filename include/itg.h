@@ -194,6 +194,15 @@ int itg_ipc_free(void* ptr);
 int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int32_t border, int32_t sides,
                    void* stream);
 
+/* Output stage of test_sample.py:75-79: `save_image(img * 0.5 + 0.5, path)` quantises the fp32 image with
+ * torchvision's `mul(255).add_(0.5).clamp_(0, 255).to(uint8)` after the `* 0.5 + 0.5`, on the host.  This does the
+ * same arithmetic (same fp32 operations in the same order, no FMA contraction: bit-identical bytes) on the device, so
+ * that 1 byte instead of 4 crosses PCIe per sample.  img: planar fp32 (c, h, w) with `row_pitch` floats between rows
+ * and `plane_pitch` floats between channels (a cropped view of the Generator's output buffer); out: interleaved
+ * (h, w, c) uint8, contiguous -- the layout PIL / image encoders take.  c <= 4. */
+int itg_image_to_u8(const float* img, int32_t c, int32_t h, int32_t w, int64_t row_pitch, int64_t plane_pitch,
+                    uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

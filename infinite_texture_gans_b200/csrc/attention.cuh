@@ -295,6 +295,23 @@ __global__ void __launch_bounds__(1024) halo_xchg_kernel(const HaloXchgParams p)
 
 __global__ void step_advance_kernel(int* step) { *step += 1; }
 
+// test_sample.py:78 + torchvision save_image: uint8 = trunc(clamp((x * 0.5 + 0.5) * 255 + 0.5, 0, 255)), every step rounded to fp32
+__global__ void image_to_u8_kernel(const float* __restrict__ img, int c, int h, int w, long long row_pitch, long long plane_pitch,
+                                   uint8_t* __restrict__ out) {
+  const size_t total = (size_t)h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+    const float* px = img + (size_t)y * row_pitch + x;
+    uint8_t* o = out + i * c;
+    for (int k = 0; k < c; ++k) {
+      float v = __fadd_rn(__fmul_rn(px[(size_t)k * plane_pitch], 0.5f), 0.5f);
+      v = __fadd_rn(__fmul_rn(v, 255.f), 0.5f);
+      v = fminf(fmaxf(v, 0.f), 255.f);
+      o[k] = (uint8_t)(int)v;                              // .to(uint8) truncates
+    }
+  }
+}
+
 // F.pad(x, (1,1,1,1), mode) on the frame of a grid tensor; sides: bit0 top, bit1 bottom, bit2 left, bit3 right
 template <typename T>
 __global__ void fill_frame_kernel(T* __restrict__ t, int h, int w, int c, int border, int sides) {

@@ -646,4 +646,13 @@ int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int3
   return ITG_OK;
 }
 
+int itg_image_to_u8(const float* img, int32_t c, int32_t h, int32_t w, int64_t row_pitch, int64_t plane_pitch, uint8_t* out, void* stream) {
+  if (!img || !out || c < 1 || c > 4 || h < 1 || w < 1 || row_pitch < w || plane_pitch < (int64_t)h * row_pitch - (row_pitch - w))
+    return fail(ITG_ERR_INVALID, "image_to_u8: bad arguments");
+  const int blocks = blocks_for((size_t)h * w, 256);
+  itg::image_to_u8_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, c, h, w, row_pitch, plane_pitch, out);
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
 }  // extern "C"

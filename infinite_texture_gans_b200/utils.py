@@ -176,6 +176,27 @@ def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, nu
 
 
 # ------------------------------------------------------------------------------------------------
+# output stage
+# ------------------------------------------------------------------------------------------------
+def image_to_uint8(img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-side output stage of test_sample.py:75-79: the bytes `torchvision.utils.save_image(img * 0.5 + 0.5, ...)` would write,
+    i.e. `(img * 0.5 + 0.5).mul(255).add_(0.5).clamp_(0, 255).to(uint8)` as an interleaved (H, W, C) uint8 device tensor, bit-identical
+    to the host computation.  img: (1, C, H, W) or (C, H, W) fp32 CUDA tensor; row / channel strides are honoured (cropped views of the
+    Generator's output buffer), the innermost stride must be 1."""
+    x = img[0] if img.dim() == 4 else img
+    if x.dim() != 3 or x.dtype != torch.float32 or not x.is_cuda or x.stride(2) != 1:
+        raise ValueError("image_to_uint8 takes a (1, C, H, W) / (C, H, W) fp32 CUDA tensor with unit innermost stride")
+    c, h, w = x.shape
+    if out is None:
+        out = torch.empty((h, w, c), dtype=torch.uint8, device=x.device)
+    elif tuple(out.shape) != (h, w, c) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError(f"out must be a contiguous ({h}, {w}, {c}) uint8 tensor on {x.device}")
+    lib = L.load()
+    L.check(lib.itg_image_to_u8(x.data_ptr(), c, h, w, x.stride(1), x.stride(0), out.data_ptr(), L.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # streaming: many textures, copies overlapped with compute
 # ------------------------------------------------------------------------------------------------
 class HostOutputPipe:
@@ -184,11 +205,11 @@ class HostOutputPipe:
     Generator pass runs while the previous image crosses PCIe; `wait(slot)` blocks until that image is on the host.
     A slot's host tensor is overwritten `depth` pushes later."""
 
-    def __init__(self, shape, device, depth: int = 3):
-        self.depth = depth
+    def __init__(self, shape, device, depth: int = 3, dtype: torch.dtype = torch.float32):
+        self.depth, self.dtype = depth, dtype
         self.copy_stream = torch.cuda.Stream(device)
-        self.stage = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(depth)]
-        self.host = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.stage = [torch.empty(shape, dtype=dtype, device=device) for _ in range(depth)]
+        self.host = [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(depth)]
         self.ready = [torch.cuda.Event() for _ in range(depth)]      # image of the slot is complete in self.stage
         self.done = [torch.cuda.Event() for _ in range(depth)]       # ... and in self.host
         self.k = 0
@@ -199,7 +220,10 @@ class HostOutputPipe:
         cur = torch.cuda.current_stream()
         if self.k > self.depth:
             cur.wait_event(self.done[s])                             # the slot's previous image has left the device
-        self.stage[s].copy_(img)                                     # after this the engine may overwrite its output buffer
+        if self.dtype == torch.uint8:
+            image_to_uint8(img, out=self.stage[s])                   # quantise on the device: 1 byte per sample crosses PCIe
+        else:
+            self.stage[s].copy_(img)                                 # after this the engine may overwrite its output buffer
         self.ready[s].record(cur)
         self.copy_stream.wait_event(self.ready[s])
         with torch.cuda.stream(self.copy_stream):
@@ -213,21 +237,27 @@ class HostOutputPipe:
 
 
 def generate_textures(netG, noises, output_resolution_height: int, output_resolution_width: int, base_res: int = 4,
-                      num_patches_height: int = 3, num_patches_width: int = 3, graph: bool = True):
+                      num_patches_height: int = 3, num_patches_width: int = 3, graph: bool = True, out_format: str = "float32"):
     """Iterator over host-resident (1, img_ch, H, W) fp32 textures, one per element of `noises`
     (each `(z_full, maps_full)` as drawn by `draw_noise`, ideally in pinned memory).  Same result per texture as
     `sample_from_gen_PatchByPatch_test(..., noise=...)` with the one-shot schedule; the difference is that texture k's
     copy to the host overlaps the Generator pass of texture k+1.  A yielded tensor is a view of a pinned staging buffer
-    and stays valid until the iterator is advanced again."""
+    and stays valid until the iterator is advanced again.
+
+    out_format='uint8' yields (H, W, img_ch) uint8 images instead: the bytes test_sample.py's `save_image(img * 0.5 + 0.5, ...)`
+    writes (`image_to_uint8`), quantised on the device so that a quarter of the bytes cross PCIe."""
+    if out_format not in ("float32", "uint8"):
+        raise ValueError("out_format must be 'float32' or 'uint8'")
     G = _unwrap(netG)
     geo = patch_grid_geometry(output_resolution_height, output_resolution_width, G.n_layers_G, base_res,
                               num_patches_height, num_patches_width)
     H, W = output_resolution_height, output_resolution_width
     dev = next(G.parameters()).device
     pipes = G.__dict__.setdefault("_host_pipes", {})     # pinned staging buffers are expensive to allocate: keep them per output size
-    pipe = pipes.get((H, W, dev))
+    pipe = pipes.get((H, W, dev, out_format))
     if pipe is None:
-        pipe = pipes[(H, W, dev)] = HostOutputPipe((1, G.img_ch, H, W), dev)
+        pipe = pipes[(H, W, dev, out_format)] = (HostOutputPipe((H, W, G.img_ch), dev, dtype=torch.uint8) if out_format == "uint8"
+                                                 else HostOutputPipe((1, G.img_ch, H, W), dev))
     in_flight = []                                       # at most depth - 1 images between the Generator pass and the consumer
     for z_full, maps_full in noises:
         img = generate_full_grid(netG, z_full[:1], None if maps_full is None else [m[:1] for m in maps_full], graph=graph)

@@ -105,6 +105,35 @@ def test_streaming_textures_equal_blocking_sampler(name):
     assert not torch.equal(got[0], got[1])
 
 
+def test_device_output_stage_matches_save_image_bytes():
+    """utils.image_to_uint8 == the bytes torchvision's save_image(img * 0.5 + 0.5) hands to PIL (test_sample.py:75-79), bit for bit:
+    (img * 0.5 + 0.5).mul(255).add_(0.5).clamp_(0, 255).to(uint8), HWC -- on values inside and outside [-1, 1], on a cropped view, and
+    through generate_textures(out_format='uint8')."""
+    import infinite_texture_gans_b200 as itg
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 3, 75, 133, generator=g) * 0.8
+    x[0, 0, :4, :4] = torch.tensor([-1.0, 1.0, 0.0, 1e-3]).repeat(4, 1)
+    x[0, 1, 5, :6] = torch.tensor([-3.0, 3.0, float("inf"), -float("inf"), 0.999999, -0.999999])
+    want = lambda t: (t[0] * 0.5 + 0.5).mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8)
+    xd = x.cuda()
+    assert torch.equal(itg.utils.image_to_uint8(xd).cpu(), want(x))
+    view = xd[:, :, 3:70, 10:101]                                       # strided view, like the [:H, :W] crop of the output buffer
+    assert torch.equal(itg.utils.image_to_uint8(view).cpu(), want(x[:, :, 3:70, 10:101]))
+    one = xd[:, :1]
+    assert torch.equal(itg.utils.image_to_uint8(one).cpu(), want(x[:, :1]))
+    with pytest.raises(ValueError):
+        itg.utils.image_to_uint8(x)                                      # host tensor: no CPU fallback
+
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn5_gamma0_rep")
+    net = make_generator(kw, sd, "fp16", "cuda")
+    H, W = int(d["H"]) - 3, int(d["W"]) - 7
+    z2 = torch.randn(z.shape, generator=g)
+    f32 = [t.clone() for t in itg.utils.generate_textures(net, [(z, maps), (z2, maps)], H, W)]
+    u8 = [t.clone() for t in itg.utils.generate_textures(net, [(z, maps), (z2, maps)], H, W, out_format="uint8")]
+    for a, b in zip(f32, u8):
+        assert b.shape == (H, W, 3) and b.dtype == torch.uint8 and torch.equal(b, want(a))
+
+
 @pytest.mark.parametrize("kw,th,tw", [
     (dict(z_dim=128, G_ch=52, n_layers_G=6, attention=True, leak=0.02, type_norm="BN", outer_padding="replicate"), 2, 4),
     (dict(z_dim=128, G_ch=52, n_layers_G=5, attention=True, leak=0.02, type_norm="SSM", outer_padding="replicate"), 3, 3),
