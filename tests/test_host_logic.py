@@ -131,6 +131,19 @@ def test_missing_library_fails_loudly(monkeypatch):
         L.load()
 
 
+def test_output_stage_and_streaming_reject_host_tensors():
+    """The device-side output stage and the streaming sampler validate their arguments before touching the library and have no host path."""
+    import infinite_texture_gans_b200 as itg
+    with pytest.raises(ValueError, match="CUDA"):
+        itg.utils.image_to_uint8(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(ValueError, match="fp32"):
+        itg.utils.image_to_uint8(torch.zeros(1, 3, 8, 8, dtype=torch.float16))
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
+    net = make_generator(kw, sd, "fp16")                     # left on the CPU
+    with pytest.raises(ValueError, match="out_format"):
+        next(itg.utils.generate_textures(net, [(z, maps)], 64, 64, out_format="png"))
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "infinite_texture_gans_b200")
     for f in os.listdir(pkg):
