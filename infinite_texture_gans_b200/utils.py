@@ -236,12 +236,56 @@ class HostOutputPipe:
         return self.host[slot]
 
 
+class NoiseUploader:
+    """Host -> device upload of the NEXT texture's noise on a side stream while the current pass computes: two device
+    staging slots per plan; `upload(noise)` starts the copies, `feed()` makes the current stream wait for the oldest
+    pending upload and moves it (device to device) into the plan's static input buffers."""
+
+    def __init__(self, plan, device):
+        self.plan = plan
+        self.stream = torch.cuda.Stream(device)
+        self.z = [torch.empty_like(plan.z_in) for _ in range(2)]
+        self.maps = [[torch.empty_like(m) for m in plan.maps_in] for _ in range(2)]
+        self.uploaded = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [None, None]
+        self.head = self.tail = 0                        # uploads started / fed
+
+    def upload(self, noise) -> None:
+        z_full, maps_full = noise
+        s = self.head % 2
+        if self.head - self.tail >= 2:
+            raise RuntimeError("NoiseUploader: both staging slots are pending")
+        self.head += 1
+        if len(self.maps[s]) and (maps_full is None or len(maps_full) < len(self.maps[s])):
+            raise ValueError("SSM Generator needs one noise map per level (utils.py:237-256)")
+        if self.consumed[s] is not None:
+            self.stream.wait_event(self.consumed[s])     # the slot's previous content has been moved into the plan
+        with torch.cuda.stream(self.stream):
+            z = z_full[0] if z_full.dim() == 4 else z_full
+            if tuple(z.shape) != tuple(self.z[s].shape):
+                raise ValueError(f"z has shape {tuple(z.shape)}, the {self.plan.th}x{self.plan.tw} patch grid needs {tuple(self.z[s].shape)}")
+            self.z[s].copy_(z, non_blocking=True)
+            for dst, m in zip(self.maps[s], maps_full or ()):
+                dst.copy_(m[0, 0] if m.dim() == 4 else m, non_blocking=True)
+            self.uploaded[s].record(self.stream)
+
+    def feed(self) -> None:
+        s = self.tail % 2
+        self.tail += 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.uploaded[s])
+        self.plan.set_inputs(self.z[s], self.maps[s] if self.maps[s] else None)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.consumed[s] = ev
+
+
 def generate_textures(netG, noises, output_resolution_height: int, output_resolution_width: int, base_res: int = 4,
                       num_patches_height: int = 3, num_patches_width: int = 3, graph: bool = True, out_format: str = "float32"):
     """Iterator over host-resident (1, img_ch, H, W) fp32 textures, one per element of `noises`
     (each `(z_full, maps_full)` as drawn by `draw_noise`, ideally in pinned memory).  Same result per texture as
     `sample_from_gen_PatchByPatch_test(..., noise=...)` with the one-shot schedule; the difference is that texture k's
-    copy to the host overlaps the Generator pass of texture k+1.  A yielded tensor is a view of a pinned staging buffer
+    copy to the host and texture k+2's noise upload overlap the Generator pass of texture k+1.  A yielded tensor is a view of a pinned staging buffer
     and stays valid until the iterator is advanced again.
 
     out_format='uint8' yields (H, W, img_ch) uint8 images instead: the bytes test_sample.py's `save_image(img * 0.5 + 0.5, ...)`
@@ -258,9 +302,27 @@ def generate_textures(netG, noises, output_resolution_height: int, output_resolu
     if pipe is None:
         pipe = pipes[(H, W, dev, out_format)] = (HostOutputPipe((H, W, G.img_ch), dev, dtype=torch.uint8) if out_format == "uint8"
                                                  else HostOutputPipe((1, G.img_ch, H, W), dev))
+    it = iter(noises)
+    nxt = next(it, None)
+    if nxt is None:
+        return
+    b = G.cfg.base_res
+    th, tw = (nxt[0].shape[-2] - 2) // b, (nxt[0].shape[-1] - 2) // b
+    eng = G.engine()
+    plan = eng.plan(th, tw, L.IMG_MERGED)
+    ups = G.__dict__.setdefault("_noise_uploaders", {})
+    up = ups.get((th, tw, dev))
+    if up is None or up.plan is not plan:
+        up = ups[(th, tw, dev)] = NoiseUploader(plan, dev)
+    up.head = up.tail = 0
+    up.upload(nxt)
     in_flight = []                                       # at most depth - 1 images between the Generator pass and the consumer
-    for z_full, maps_full in noises:
-        img = generate_full_grid(netG, z_full[:1], None if maps_full is None else [m[:1] for m in maps_full], graph=graph)
+    while nxt is not None:
+        up.feed()                                        # this texture's noise: staged on the device during the previous pass
+        img = eng.replay(th, tw, L.IMG_MERGED) if graph else plan.run()
+        nxt = next(it, None)
+        if nxt is not None:
+            up.upload(nxt)                               # the next texture's noise crosses PCIe while this pass computes
         in_flight.append(pipe.push(img[:, :, :H, :W]))
         if len(in_flight) == pipe.depth:
             yield pipe.wait(in_flight.pop(0))
