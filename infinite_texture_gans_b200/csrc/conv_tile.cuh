@@ -9,13 +9,14 @@
 //     up-sampling) are nine shifted views of that one tile: the local-padding halo gather is a 16-byte-granular
 //     offset in the MMA's shared-memory descriptor (no-swizzle K-major layout, 8 x 16 B core matrices: rows =
 //     8 consecutive pixels of a tile row, SBO = one halo-tile row, LBO = one plane).  The planes are filled by
-//     three producer warps with 16-byte cp.async (zero-fill outside the buffer), several tiles in flight;
-//   * CTAs are persistent (grid = SM count): producer warps, the MMA warp and two groups of epilogue warps run
-//     as a pipeline over the tile sequence (multi-stage input ring, double-buffered TMEM accumulators), so the
-//     epilogue of tile i overlaps the loads and MMAs of tiles i+1, i+2;
-//   * the MMA warp runs warp-uniform (descriptors live in uniform registers, one elected lane issues), the conv
-//     mode and the epilogue variant are template parameters: measured on B200, the single-thread issue loop of
-//     the first version cost ~320 cycles per tcgen05.mma and was the bottleneck (profiles/r01_notes.md).
+//     a producer warp with 16-byte cp.async (zero-fill outside the buffer), up to three tiles in flight;
+//   * CTAs are persistent (grid = SM count) and run four independent pipelines {producer warp, MMA warp, four
+//     epilogue warps}, each over its own tiles with a private ring of input stages and private TMEM accumulator
+//     buffers, so the epilogue of tile i overlaps the loads and MMAs of the following tiles and every mbarrier has
+//     one arriving and one waiting party (see TILE_PIPES below);
+//   * the MMA warps run warp-uniform (one elected lane issues, predicated, no branch), the conv mode and the
+//     epilogue variant are template parameters: measured on B200, the single-thread issue loop of the first
+//     version cost ~320 cycles per tcgen05.mma and was the bottleneck (profiles/r01_notes.md).
 #pragma once
 #include <type_traits>
 #include "conv_umma.cuh"
