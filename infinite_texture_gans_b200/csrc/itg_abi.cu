@@ -87,14 +87,20 @@ EncodeTiledFn get_encode() {
 }
 
 
+constexpr int MAX_DEVICES = 64;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  return dev;
+}
+// per-device caches: one process may drive several GPUs (function attributes and SM counts are per device)
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+  static int n[MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // tile width for an M-grid of width w: as wide as possible (coalesced rows) but no wider than the grid
@@ -301,10 +307,11 @@ int launch_umma(const itg_conv_desc& d, cudaStream_t st) {
   }
 #define ITG_UMMA_LAUNCH(FL)                                                                                            \
   do {                                                                                                                 \
-    static bool attr_set = false;                                                                                      \
-    if (!attr_set) {                                                                                                   \
+    static bool attr_set[MAX_DEVICES] = {false};                                                                       \
+    const int dev_ = current_device();                                                                                 \
+    if (!attr_set[dev_]) {                                                                                             \
       ITG_CUDA(cudaFuncSetAttribute(itg::conv_umma_kernel<T, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr_set = true;                                                                                                 \
+      attr_set[dev_] = true;                                                                                           \
     }                                                                                                                  \
     ITG_CUDA(launch_pdl_cluster(itg::conv_umma_kernel<T, FL>, dim3(grid), dim3(itg::UMMA_THREADS), smem, st, p.cluster, tm_a, tm_b, p)); \
   } while (0)
@@ -402,10 +409,11 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   }
 #define ITG_TILE_LAUNCH(FL, MD)                                                                                       \
   do {                                                                                                                \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
+    static bool attr_set[MAX_DEVICES] = {false};                                                                      \
+    const int dev_ = current_device();                                                                                \
+    if (!attr_set[dev_]) {                                                                                            \
       ITG_CUDA(cudaFuncSetAttribute(itg::conv_tile_kernel<T, FL, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr_set = true;                                                                                                \
+      attr_set[dev_] = true;                                                                                          \
     }                                                                                                                 \
     ITG_CUDA(launch_pdl(itg::conv_tile_kernel<T, FL, MD>, dim3(grid), dim3(itg::TILE_THREADS), smem, st, p));         \
   } while (0)
@@ -511,7 +519,9 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
     q.w_theta = w_theta; q.b_theta = b_theta; q.w_phi = w_phi; q.b_phi = b_phi; q.w_g = w_g; q.b_g = b_g;
     q.w_o = w_o; q.b_o = b_o; q.gamma = gamma; q.out_raw = out_raw; q.out_act = out_act; q.scale = scale; q.shift = shift;
     q.leak = leak; q.border = border;
-    static bool attr_h = false, attr_b = false;
+    static bool attr_hd[MAX_DEVICES] = {false}, attr_bd[MAX_DEVICES] = {false};
+    bool& attr_h = attr_hd[current_device()];
+    bool& attr_b = attr_bd[current_device()];
     if (dtype == ITG_F16) {
       if (!attr_h) { ITG_CUDA(cudaFuncSetAttribute(itg::attention_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, itg::AM_SMEM)); attr_h = true; }
       ITG_CUDA(launch_pdl(itg::attention_mma_kernel<__half>, dim3(th * tw < sm_count() ? th * tw : sm_count()), dim3(256), itg::AM_SMEM, st, q));

@@ -530,25 +530,32 @@ class Engine:
                 img_layout: int = L.IMG_MERGED, graph: bool = False) -> torch.Tensor:
         """One-shot Generator forward of the whole th x tw grid.  Returns the plan's output buffer
         ((1, img_ch, th*P, tw*P) merged or (th*tw, img_ch, P, P) patches); it is overwritten by the next call."""
-        p = self.plan(th, tw, img_layout)
-        p.set_inputs(z, maps)
-        if graph and self.device.type == "cuda":
-            self.replay(th, tw, img_layout)
-        else:
-            p.run()
+        with self._on_device():
+            p = self.plan(th, tw, img_layout)
+            p.set_inputs(z, maps)
+            if graph and self.device.type == "cuda":
+                self.replay(th, tw, img_layout)
+            else:
+                p.run()
         return p.out
+
+    def _on_device(self):
+        """Launches go to the current stream of the CURRENT device: make the engine's device current (one process may drive several GPUs)."""
+        import contextlib
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
 
     def replay(self, th: int, tw: int, img_layout: int = L.IMG_MERGED) -> torch.Tensor:
         """Run the plan's launch list from a captured CUDA graph (inputs already in plan.z_in / plan.maps_in)."""
         key = (th, tw, img_layout)
-        p = self.plan(th, tw, img_layout)
-        g = self._graphs.get(key)
-        if g is None:
-            p.run()                                  # warm-up outside capture: one-time attribute / tensor-map setup
-            torch.cuda.current_stream().synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                p.run()
-            self._graphs[key] = g
-        g.replay()
+        with self._on_device():
+            p = self.plan(th, tw, img_layout)
+            g = self._graphs.get(key)
+            if g is None:
+                p.run()                              # warm-up outside capture: one-time attribute / tensor-map setup
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    p.run()
+                self._graphs[key] = g
+            g.replay()
         return p.out

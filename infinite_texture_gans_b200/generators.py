@@ -134,7 +134,8 @@ class ResidualPatchGenerator(nn.Module):
                     else:
                         m = m[n, 0]
                     mp.append(m.float())
-            plan.set_inputs(z[n].float(), mp)
-            plan.run(self._seq.hooks(plan, image_location) if N == 1 else None)
-            outs.append(plan.out.clone())
+            with eng._on_device():                    # launches go to the current stream of the engine's device
+                plan.set_inputs(z[n].float(), mp)
+                plan.run(self._seq.hooks(plan, image_location) if N == 1 else None)
+                outs.append(plan.out.clone())
         return outs[0] if N == 1 else torch.cat(outs, 0)

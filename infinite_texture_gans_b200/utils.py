@@ -315,15 +315,17 @@ def generate_textures(netG, noises, output_resolution_height: int, output_resolu
     if up is None or up.plan is not plan:
         up = ups[(th, tw, dev)] = NoiseUploader(plan, dev)
     up.head = up.tail = 0
-    up.upload(nxt)
+    with torch.cuda.device(dev):                         # (never across a yield: the consumer keeps its own current device)
+        up.upload(nxt)
     in_flight = []                                       # at most depth - 1 images between the Generator pass and the consumer
     while nxt is not None:
-        up.feed()                                        # this texture's noise: staged on the device during the previous pass
-        img = eng.replay(th, tw, L.IMG_MERGED) if graph else plan.run()
-        nxt = next(it, None)
-        if nxt is not None:
-            up.upload(nxt)                               # the next texture's noise crosses PCIe while this pass computes
-        in_flight.append(pipe.push(img[:, :, :H, :W]))
+        with torch.cuda.device(dev):
+            up.feed()                                    # this texture's noise: staged on the device during the previous pass
+            img = eng.replay(th, tw, L.IMG_MERGED) if graph else plan.run()
+            nxt = next(it, None)
+            if nxt is not None:
+                up.upload(nxt)                           # the next texture's noise crosses PCIe while this pass computes
+            in_flight.append(pipe.push(img[:, :, :H, :W]))
         if len(in_flight) == pipe.depth:
             yield pipe.wait(in_flight.pop(0))
     for slot in in_flight:

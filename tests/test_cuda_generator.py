@@ -178,6 +178,22 @@ def test_two_gpu_band_split_equals_single_gpu():
     assert "max|bands - single GPU| = 0.000e+00" in r.stdout
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or not __import__("os").environ.get("ITG_TEST_MULTI_DEVICE"),
+                    reason="opt-in (ITG_TEST_MULTI_DEVICE=1, two GPUs): the supported model is one process per GPU")
+def test_one_process_two_devices():
+    """One process driving two GPUs (per-device function attributes / SM counts in the C ABI, device guards in the engine): the same
+    Generator on cuda:0 and cuda:1 gives the same image.  Passes on its own; kept opt-in because the product runs one process per
+    GPU and this mode has only been exercised in isolation."""
+    import infinite_texture_gans_b200 as itg
+    d, kw, ocfg, sd, z, maps = load_case("gen_241_3x3")
+    a = itg.utils.generate_full_grid(make_generator(kw, sd, "fp16", "cuda:0"), z).cpu()
+    b = itg.utils.generate_full_grid(make_generator(kw, sd, "fp16", "cuda:1"), z).cpu()       # current device stays cuda:0
+    c = itg.utils.generate_full_grid(make_generator(kw, sd, "fp16", "cuda:1"), z, graph=True).cpu()
+    assert torch.equal(b, c)
+    assert torch.equal(a, b)
+    compare_with_golden(d, "one", b, TOL["fp16"])
+
+
 def test_cli_end_to_end(tmp_path):
     """test_sample.py flow (test_sample.py:11-79): checkpoint {'args': Namespace, 'netG_state_dict'} with DataParallel
     'module.' prefixes -> image file next to the checkpoint; the saved 8-bit image matches the oracle to 8-bit precision."""
