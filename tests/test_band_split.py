@@ -49,7 +49,8 @@ def _rank_main(rank, world, port, name, splits, out_dir):
 
 
 @pytest.mark.parametrize("name,splits", [("gen_bn4_att_rep", (0, 3, 5)), ("gen_ssm4_att_rep", (0, 1, 3)),
-                                         ("gen_bn4_noatt_const_crop", (0, 2, 3))])
+                                         ("gen_bn4_noatt_const_crop", (0, 2, 3)),
+                                         ("gen_bn4_att_rep", (0, 2, 3, 5))])           # three ranks: the middle one has two neighbours
 def test_two_rank_band_split_equals_single_process(name, splits, tmp_path):
     world = len(splits) - 1
     mp.spawn(_rank_main, args=(world, _free_port(), name, splits, str(tmp_path)), nprocs=world, join=True)
