@@ -405,7 +405,7 @@ def main():
     roof, cpu_base = None, None
     if rank == 0:
         times = launch_profile(plan)
-        conv_ms = sum(tm for (kind, op), tm in zip(plan.ops, times) if kind == "conv")
+        conv_ms = sum(tm for (kind, op), tm in zip(plan.ops, times) if kind in ("conv", "ssm"))
         all_ms = sum(times)
         total_flops = flops_per_patch(cfg) * th * tw
         att_flops = 0.0
@@ -430,7 +430,7 @@ def main():
         if args.profile_out:
             rows = []
             for (kind, op), tm in zip(plan.ops, times):
-                name = getattr(op, "name", kind) if kind in ("conv", "att") else kind
+                name = getattr(op, "name", kind) if kind in ("conv", "att", "ssm") else kind
                 rows.append({"launch": name, "kind": kind, "ms": tm})
             json.dump({"workload": desc, "precision": args.precision, "launches": rows}, open(args.profile_out, "w"), indent=1)
         if world == 1 and not args.no_cpu_baseline:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ITG_ABI_VERSION 1
+#define ITG_ABI_VERSION 2
 
 enum itg_status {
   ITG_OK = 0,
@@ -146,6 +146,45 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
                       const float* w_g, const float* b_g, const float* w_o, const float* b_o, const float* gamma,
                       void* out_raw, void* out_act, const float* scale, const float* shift, float leak,
                       int32_t border, void* stream);
+
+/* StochasticSpatialModulation.forward (models/layers.py:228-234) as one launch:
+ *   m1 = relu(conv3x3_valid(map) + b1)            mlp_shared (layers.py:220-222, 229), 1 -> 128 channels
+ *   [gamma|beta] = conv3x3_valid(m1) + b2         embed (layers.py:224, 230), 128 -> 2C channels
+ *   out = [act]((1 + gamma) * (x - mean) * rstd + beta)       (layers.py:228, 231-233; the activation of ResBlockGenerator.forward,
+ *                                                               layers.py:303-312, unless `linear`, which is the shortcut's bn3)
+ * The 128-channel hidden map stays on chip (16-bit operand types only; the fp32 exact mode runs the two convs as itg_conv_fwd launches).
+ *   map     : fp32 noise map of this level, (h+4) x (w+4) values, `map_pitch` floats per row (utils.py:246, map_dim = 1 as in test_sample.py:56)
+ *   w_mlp   : [128][16] operand dtype, K-major: columns 0..8 = mlp_shared.0.weight[n][0][ky][kx] (tap ky*3+kx), columns 9 and 10 = the bias
+ *             mlp_shared.0.bias[n] split into a 16-bit hi + lo pair (the kernel feeds constant ones in those two K slots), rest zero
+ *   w_embed : [9][n_pad][128] operand dtype, rows interleaved (gamma_c, beta_c) per stored channel c (2*c <= n_pad, n_pad % 16 == 0)
+ *   b_embed : [n_pad] fp32, same interleaving
+ *   x       : grid tensor to modulate, x_c storage channels, interior x_h x x_w, read at (y >> x_shift, x >> x_shift)
+ *             (x_shift = 1: the nearest-2x up-sampling of generators.py:95-111 folded into the addressing)
+ *   mean / rstd : [c] running_mean and 1/sqrt(running_var + eps) of the affine-free BatchNorm (layers.py:218)
+ *   out     : grid tensor h x w x c, frame written per `border` */
+typedef struct itg_ssm_desc {
+  int32_t dtype;        /* ITG_F16 | ITG_BF16 */
+  int32_t border;       /* itg_border applied to out's frame */
+  int32_t h, w;         /* interior size of out */
+  int32_t c;            /* storage channels of out (multiple of 8) */
+  int32_t n_pad;        /* GEMM columns of the embed conv */
+  const float* map;
+  int32_t map_pitch;
+  int32_t x_shift;
+  const void* w_mlp;
+  const void* w_embed;
+  const float* b_embed;
+  const void* x;
+  int32_t x_c, x_h, x_w;
+  int32_t linear;       /* 1: no activation */
+  const float* mean;
+  const float* rstd;
+  void* out;
+  float leak;
+  int32_t reserved;
+} itg_ssm_desc;
+int itg_ssm_desc_size(void);
+int itg_ssm_fwd(const itg_ssm_desc* desc, void* stream);
 
 /* Host-supplied noise -> grid tensor.  src: fp32 planar (C, H, W) (the z grid with its random 1-px ring,
  * utils.py:228, or an SSM map, utils.py:246); dst: (H x W x dst_c) channels-last in `dtype`, channels

@@ -28,7 +28,7 @@ TORCH_OF = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 
 EXPORTS = ("itg_version", "itg_last_error", "itg_conv_desc_size", "itg_conv_fwd", "itg_attention_fwd",
            "itg_pack_nchw", "itg_pack_map_taps", "itg_copy_rect", "itg_fill_frame", "itg_halo_exchange", "itg_step_advance",
-           "itg_ipc_alloc", "itg_ipc_open", "itg_ipc_close", "itg_ipc_free", "itg_image_to_u8")
+           "itg_ipc_alloc", "itg_ipc_open", "itg_ipc_close", "itg_ipc_free", "itg_image_to_u8", "itg_ssm_fwd", "itg_ssm_desc_size")
 
 
 class ConvDesc(C.Structure):
@@ -46,6 +46,17 @@ class ConvDesc(C.Structure):
         ("out_raw", C.c_void_p), ("out_act", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("leak", C.c_float), ("act_linear", C.c_int32), ("out_f32", C.c_void_p), ("out_img", C.c_void_p),
         ("img_c", C.c_int32), ("img_layout", C.c_int32), ("patch", C.c_int32),
+    ]
+
+
+class SsmDesc(C.Structure):
+    """Mirror of `struct itg_ssm_desc` (include/itg.h), same field order."""
+    _fields_ = [
+        ("dtype", C.c_int32), ("border", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("n_pad", C.c_int32),
+        ("map", C.c_void_p), ("map_pitch", C.c_int32), ("x_shift", C.c_int32),
+        ("w_mlp", C.c_void_p), ("w_embed", C.c_void_p), ("b_embed", C.c_void_p),
+        ("x", C.c_void_p), ("x_c", C.c_int32), ("x_h", C.c_int32), ("x_w", C.c_int32), ("linear", C.c_int32),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("out", C.c_void_p), ("leak", C.c_float), ("reserved", C.c_int32),
     ]
 
 
@@ -96,6 +107,11 @@ def load() -> C.CDLL:
     lib.itg_fill_frame.argtypes = [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]
     lib.itg_image_to_u8.restype = C.c_int
     lib.itg_image_to_u8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.itg_ssm_desc_size.restype = C.c_int
+    lib.itg_ssm_fwd.restype = C.c_int
+    lib.itg_ssm_fwd.argtypes = [C.POINTER(SsmDesc), C.c_void_p]
+    if lib.itg_ssm_desc_size() != C.sizeof(SsmDesc):
+        raise ItgError(f"itg_ssm_desc layout mismatch: library {lib.itg_ssm_desc_size()} B, binding {C.sizeof(SsmDesc)} B")
     if lib.itg_conv_desc_size() != C.sizeof(ConvDesc):
         raise ItgError(f"itg_conv_desc layout mismatch: library {lib.itg_conv_desc_size()} B, binding {C.sizeof(ConvDesc)} B")
     _lib = lib

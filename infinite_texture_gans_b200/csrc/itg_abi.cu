@@ -12,6 +12,7 @@
 #include "conv_direct.cuh"
 #include "conv_umma.cuh"
 #include "conv_tile.cuh"
+#include "ssm_fused.cuh"
 
 namespace {
 
@@ -457,6 +458,62 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
+// StochasticSpatialModulation as one launch (ssm_fused.cuh)
+template <typename T>
+int launch_ssm(const itg_ssm_desc& d, cudaStream_t st) {
+  itg::SsmParams p;
+  memset(&p, 0, sizeof(p));
+  p.h = d.h; p.w = d.w;
+  p.tiles_x = (d.w + itg::TILE_W - 1) / itg::TILE_W;
+  p.ntiles = p.tiles_x * ((d.h + itg::TILE_H - 1) / itg::TILE_H);
+  p.map = d.map; p.map_pitch = d.map_pitch;
+  p.w1 = d.w_mlp; p.w2 = d.w_embed;
+  p.n_pad = d.n_pad;
+  // N blocking: the weights of one block (all taps, K = 128) stay in shared memory for the whole launch
+  p.nblocks = (d.n_pad + itg::SSM_NBLK_MAX - 1) / itg::SSM_NBLK_MAX;
+  p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 15) / 16 * 16;
+  const int sms = sm_count();
+  if (p.nblocks > sms) return fail(ITG_ERR_UNSUPPORTED, "ssm: %d GEMM columns need more column blocks than there are SMs", d.n_pad);
+  int nslots = sms / p.nblocks;
+  if (nslots > p.ntiles) nslots = p.ntiles;
+  const int grid = nslots * p.nblocks;
+  const uint32_t fmt = (d.dtype == ITG_BF16) ? 1u : 0u;
+  p.idesc_mlp = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(itg::SSM_K >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc_emb = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_blk >> 3) << 17) | ((128u >> 4) << 24);
+  itg::EpiParams& ep = p.ep;
+  ep.out_h = d.h; ep.out_w = d.w; ep.out_c = d.c; ep.n_pad = d.n_pad;
+  ep.bias = d.b_embed;
+  ep.mod_x = d.x; ep.mod_c = d.x_c; ep.mod_shift = d.x_shift; ep.mod_h = d.x_h; ep.mod_w = d.x_w;
+  ep.mod_mean = d.mean; ep.mod_rstd = d.rstd;
+  ep.out_act = d.out; ep.leak = d.leak; ep.act_linear = d.linear; ep.border = d.border;
+  static const bool dbg_on = getenv("ITG_TILE_DBG") != nullptr;      // developer aid: per-role cycle counters, synchronous
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) ITG_CUDA(cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long)));
+    ITG_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st));
+    p.dbg = dbg_buf;
+  }
+  const int smem = itg::ssm_smem_bytes(p.n_blk);
+  static bool attr_set[MAX_DEVICES] = {false};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
+    ITG_CUDA(cudaFuncSetAttribute(itg::ssm_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  ITG_CUDA(launch_pdl(itg::ssm_fused_kernel<T>, dim3(grid), dim3(itg::SSM_THREADS), smem, st, p));
+  if (dbg_on) {
+    unsigned long long hst[16];
+    ITG_CUDA(cudaStreamSynchronize(st));
+    ITG_CUDA(cudaMemcpy(hst, dbg_buf, sizeof(hst), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[itg ssm dbg] %dx%d n_pad=%d n_blk=%d nblocks=%d tiles=%d grid=%d | kcycles CTA0: mma.mlp=%.1f mma.wait_acc=%.1f mma.wait_a=%.1f mma.issue=%.1f "
+            "cvt.wait_mlp=%.1f cvt.wait_a_empty=%.1f cvt.work=%.1f epi.wait=%.1f epi.work=%.1f\n",
+            d.h, d.w, d.n_pad, p.n_blk, p.nblocks, p.ntiles, grid, hst[0] / 1e3, hst[1] / 1e3, hst[2] / 1e3, hst[3] / 1e3, hst[4] / 1e3,
+            hst[5] / 1e3, hst[6] / 1e3, hst[8] / 1e3, hst[9] / 1e3);
+  }
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
 int blocks_for(size_t total, int threads) {
   size_t b = (total + threads - 1) / threads;
   if (b > 148 * 32) b = 148 * 32;
@@ -493,6 +550,23 @@ int itg_conv_fwd(const itg_conv_desc* desc, void* stream) {
   if (d.dtype == ITG_F32) return launch_direct<float>(d, st);
   if (d.dtype == ITG_F16) return launch_direct<__half>(d, st);
   return launch_direct<__nv_bfloat16>(d, st);
+}
+
+int itg_ssm_desc_size(void) { return (int)sizeof(itg_ssm_desc); }
+
+int itg_ssm_fwd(const itg_ssm_desc* desc, void* stream) {
+  if (!desc) return fail(ITG_ERR_INVALID, "ssm: null descriptor");
+  const itg_ssm_desc& d = *desc;
+  if (d.dtype != ITG_F16 && d.dtype != ITG_BF16)
+    return fail(ITG_ERR_UNSUPPORTED, "ssm: the fused kernel needs 16-bit operands (fp32 runs mlp_shared and embed as two itg_conv_fwd launches)");
+  if (!d.map || !d.w_mlp || !d.w_embed || !d.b_embed || !d.x || !d.mean || !d.rstd || !d.out) return fail(ITG_ERR_INVALID, "ssm: null argument");
+  if (d.h < 1 || d.w < 1 || d.map_pitch < d.w + 4) return fail(ITG_ERR_INVALID, "ssm: bad geometry %dx%d, map pitch %d", d.h, d.w, d.map_pitch);
+  if (d.c % 8 || d.c <= 0 || d.n_pad % 16 || 2 * d.c > d.n_pad) return fail(ITG_ERR_INVALID, "ssm: c=%d / n_pad=%d (c %% 8 == 0, n_pad %% 16 == 0, 2c <= n_pad)", d.c, d.n_pad);
+  if (d.x_c < d.c || d.x_c % 8 || d.x_shift < 0 || d.x_shift > 1) return fail(ITG_ERR_INVALID, "ssm: x has %d storage channels, shift %d", d.x_c, d.x_shift);
+  if (((d.h - 1) >> d.x_shift) >= d.x_h || ((d.w - 1) >> d.x_shift) >= d.x_w) return fail(ITG_ERR_INVALID, "ssm: x (%dx%d) does not cover the %dx%d output at shift %d", d.x_h, d.x_w, d.h, d.w, d.x_shift);
+  if (d.border < ITG_BORDER_NONE || d.border > ITG_BORDER_CONSTANT) return fail(ITG_ERR_INVALID, "ssm: bad border %d", d.border);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d.dtype == ITG_F16 ? launch_ssm<__half>(d, st) : launch_ssm<__nv_bfloat16>(d, st);
 }
 
 int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int32_t patch, int32_t C, int32_t xc,

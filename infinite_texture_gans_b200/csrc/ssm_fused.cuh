@@ -1,0 +1,312 @@
+// StochasticSpatialModulation.forward (models/layers.py:228-234) as ONE persistent tcgen05 kernel:
+//
+//     m1          = relu(conv3x3_valid(map) + b1)          mlp_shared: 1 -> 128 channels
+//     [gamma|beta] = conv3x3_valid(m1) + b2                 embed: 128 -> 2C channels   (93 % of the SSM config's FLOPs)
+//     out         = [act]((1 + gamma) * bn0(x) + beta)      modulation (+ activation, + outer padding of the frame)
+//
+// The 128-channel hidden map m1 (256 B per pixel) never exists in global memory.  Per 16 x 8 output tile:
+//   1. a producer warp reads the tile's (16+4) x (8+4) window of the fp32 noise map and writes the nine 3x3 taps of each of
+//      the (16+2) x (8+2) halo pixels as one K = 16 operand row (taps 0..8, two constant ones that carry the bias, zeros);
+//   2. the MMA warp runs  m1_acc[halo pixel][128] = taps[halo pixel][16] x W1[128][16]^T  (two M = 128 tcgen05.mma, the bias
+//      b1 rides in the two constant K slots as an fp16 hi + lo pair) into tensor memory;
+//   3. six converter warps drain that accumulator 16 channels at a time (tcgen05.ld), apply ReLU, round to the operand type
+//      and store the values as the embed conv's A operand: 16 planes of [halo pixel][8 channels] in shared memory (the
+//      halo-tile layout of conv_tile.cuh), released plane pair by plane pair through mbarriers;
+//   4. the MMA warp accumulates the embed conv over 8 k-steps x 9 taps: the tap shift is a 16-byte-granular offset of the
+//      no-swizzle K-major A descriptor (SBO = one halo-tile row, LBO = one plane), so the tile's m1 values are produced
+//      once and read nine times from shared memory.  The embed weights of the CTA's <= 64 GEMM columns (all taps, K = 128:
+//      <= 144 KB) are parked in shared memory for the whole launch: in steady state the kernel loads nothing but the
+//      1-channel map, x and its own output.  Wider layers (N = 2C > 64) are split into N blocks over the CTAs
+//      (CTA c serves block c % nblocks; m1 is recomputed per block, which costs two small MMAs and one conversion);
+//   5. four epilogue warps drain the embed accumulator (double-buffered in TMEM) through the modulation epilogue
+//      (epilogue_ssm16, itg_common.cuh) while the next tile is being computed.
+// The plane-pair granularity of step 3/4 lets the conversion of tile i+1 trail the embed MMAs of tile i by one k-step, so
+// one 45 KB A buffer suffices next to the parked weights.  Every mbarrier has one producing and one consuming role that
+// walk its phases in order (see conv_tile.cuh for why that matters).
+#pragma once
+#include "conv_tile.cuh"
+
+namespace itg {
+
+constexpr int SSM_K = 128;                                   // nhidden of StochasticSpatialModulation (models/layers.py:220)
+constexpr int SSM_KG = SSM_K / 8;                            // 8-channel planes of the A operand
+constexpr int SSM_KSTEPS = SSM_K / 16;
+constexpr int SSM_WARPS = 12;                                // 0-3 epilogue, 4-9 converters, 10 MMA, 11 taps producer + TMEM allocator
+constexpr int SSM_THREADS = 32 * SSM_WARPS;
+constexpr int SSM_NBLK_MAX = 64;                             // GEMM columns whose weights fit shared memory next to the A planes
+constexpr int SSM_TAPS_ROWS = 256;                           // 180 halo pixels padded to two M = 128 row blocks
+constexpr int SSM_TAPS_BYTES = 2 * SSM_TAPS_ROWS * 16;       // two 8-element K groups
+constexpr int SSM_W1_BYTES = 2 * SSM_K * 16;
+constexpr int SSM_WIN_W = TILE_W + 4, SSM_WIN_H = TILE_H + 4;   // map window of one tile: 12 x 20
+constexpr int SSM_WIN_N = SSM_WIN_W * SSM_WIN_H;
+constexpr int SSM_HDR = 1024;
+constexpr int SSM_OFF_W1 = SSM_HDR;
+constexpr int SSM_OFF_TAPS = SSM_OFF_W1 + SSM_W1_BYTES;                // 2 buffers
+constexpr int SSM_OFF_WIN = SSM_OFF_TAPS + 2 * SSM_TAPS_BYTES;         // 16-bit staging of the map window
+constexpr int SSM_OFF_A = SSM_OFF_WIN + 512;                           // 16 planes of 180 halo pixels x 16 B
+constexpr int SSM_OFF_W2 = SSM_OFF_A + SSM_KG * PLANE_BYTES;           // [tap 9][k-group 16][n_blk][16 B]
+constexpr int SSM_TMEM_MLP = 256;                                      // TMEM columns 256..511: the two m1 row blocks; 0..2*n_blk: embed accumulators
+static_assert(SSM_WIN_N * 2 <= 512, "map window staging");
+static_assert(SSM_OFF_A % 128 == 0 && SSM_OFF_W2 % 128 == 0, "operand alignment");
+
+__host__ __device__ constexpr int ssm_smem_bytes(int n_blk) { return SSM_OFF_W2 + 9 * SSM_KG * n_blk * 16 + 1024; }
+
+struct SsmParams {
+  int h, w;                 // interior size of the modulated tensor / output
+  int tiles_x, ntiles;
+  const float* map;         // fp32 (h+4) x (w+4) noise map of this level (utils.py:246), `map_pitch` floats per row
+  int map_pitch;
+  const void* w1;           // [128][16] operand dtype: mlp_shared taps 0..8, bias hi / lo in columns 9 / 10
+  const void* w2;           // [9][n_pad][128] operand dtype (gamma / beta rows interleaved, packing.pack_ssm_embed)
+  int n_pad, n_blk, nblocks;
+  uint32_t idesc_mlp, idesc_emb;
+  unsigned long long* dbg;  // optional cycle counters of CTA 0 (ITG_TILE_DBG=1)
+  EpiParams ep;
+};
+
+#define ITG_SACC(slot, tvar) do { if (p.dbg) { const long long now_ = clock64(); dacc[slot] += (unsigned long long)(now_ - tvar); tvar = now_; } } while (0)
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SSM_THREADS, 1)
+ssm_fused_kernel(const SsmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_taps_full = sbase;            // [2]  producer (32 lanes) -> MMA
+  const uint32_t bar_taps_empty = sbase + 16;      // [2]  MMA commit -> producer
+  const uint32_t bar_mlp_full = sbase + 32;        //      MMA commit -> converters
+  const uint32_t bar_mlp_empty = sbase + 40;       //      converters (6 warps) -> MMA
+  const uint32_t bar_a_full = sbase + 64;          // [8]  converters (6 warps) -> MMA, one per plane pair
+  const uint32_t bar_a_empty = sbase + 128;        // [8]  MMA commit -> converters
+  const uint32_t bar_acc_full = sbase + 192;       // [2]  MMA commit -> epilogue
+  const uint32_t bar_acc_empty = sbase + 208;      // [2]  epilogue (4 warps) -> MMA
+  const uint32_t tmem_slot = sbase + 224;
+
+  const int nb = (int)blockIdx.x % p.nblocks;      // this CTA's block of GEMM columns (weights resident)
+  const int slot = (int)blockIdx.x / p.nblocks, nslots = (int)gridDim.x / p.nblocks;
+  const int n_my = slot < p.ntiles ? (p.ntiles - slot + nslots - 1) / nslots : 0;
+
+  pdl_launch_dependents();
+  if (warp == 10 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_taps_full + 8 * i, 32);
+      mbar_init(bar_taps_empty + 8 * i, 1);
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 4);
+    }
+    mbar_init(bar_mlp_full, 1);
+    mbar_init(bar_mlp_empty, 6);
+    for (int i = 0; i < SSM_KSTEPS; ++i) {
+      mbar_init(bar_a_full + 8 * i, 6);
+      mbar_init(bar_a_empty + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 11) tmem_alloc(tmem_slot, 512);
+
+  // ---- park the weights (they do not depend on the previous launch): embed block [tap][k-group][n][8 ch], W1 [k-group][n][8 ch] ----
+  {
+    const T* w2 = reinterpret_cast<const T*>(p.w2);
+    const int chunks = 9 * SSM_KG * p.n_blk;
+    const uint32_t w2s = sbase + SSM_OFF_W2;
+    for (int i = threadIdx.x; i < chunks; i += SSM_THREADS) {
+      const int n = i % p.n_blk, j = (i / p.n_blk) % SSM_KG, t = i / (p.n_blk * SSM_KG);
+      const int ng = nb * p.n_blk + n;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ng < p.n_pad) v = *reinterpret_cast<const uint4*>(w2 + ((size_t)t * p.n_pad + ng) * SSM_K + j * 8);
+      sts128(w2s + (uint32_t)i * 16u, v.x, v.y, v.z, v.w);
+    }
+    const T* w1 = reinterpret_cast<const T*>(p.w1);
+    for (int i = threadIdx.x; i < 2 * SSM_K; i += SSM_THREADS) {
+      const int n = i % SSM_K, j = i / SSM_K;
+      const uint4 v = *reinterpret_cast<const uint4*>(w1 + n * 16 + j * 8);
+      sts128(sbase + SSM_OFF_W1 + (uint32_t)i * 16u, v.x, v.y, v.z, v.w);
+    }
+    for (int i = threadIdx.x; i < 2 * SSM_TAPS_BYTES / 16; i += SSM_THREADS)       // rows 180..255 of the taps operand stay zero
+      sts128(sbase + SSM_OFF_TAPS + (uint32_t)i * 16u, 0u, 0u, 0u, 0u);
+    fence_proxy_async();                                                           // generic writes -> async proxy (UMMA) reads
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                       // x (and, in a captured step, the map) of the previous launches are complete from here on
+
+  if (warp == 11) {
+    // ---- taps producer: map window -> K = 16 operand rows of the tile's 180 halo pixels ----
+    T* const win = reinterpret_cast<T*>(sptr + SSM_OFF_WIN);
+    const int map_h = p.h + 4, map_w = p.w + 4;
+    const T one_t = Op<T>::from_f(1.f);
+    const uint32_t one = (uint32_t)(*reinterpret_cast<const unsigned short*>(&one_t));     // the constant K slots that carry the bias
+    int tile = slot;
+    for (int it = 0; it < n_my; ++it, tile += nslots) {
+      const int tb = it & 1;
+      if (lane == 0) mbar_wait(bar_taps_empty + 8 * tb, (((uint32_t)it >> 1) & 1u) ^ 1u);
+      __syncwarp();
+      const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+      const int y0 = ty * TILE_H, x0 = tx * TILE_W;
+#pragma unroll
+      for (int k = 0; k < (SSM_WIN_N + 31) / 32; ++k) {
+        const int idx = lane + 32 * k;
+        if (idx < SSM_WIN_N) {
+          const int r = idx / SSM_WIN_W, c = idx - r * SSM_WIN_W;
+          const int yy = y0 + r, xx = x0 + c;
+          const float v = (yy < map_h && xx < map_w) ? p.map[(size_t)yy * p.map_pitch + xx] : 0.f;
+          win[idx] = Op<T>::from_f(v);
+        }
+      }
+      __syncwarp();
+      const uint32_t dst = sbase + SSM_OFF_TAPS + (uint32_t)tb * SSM_TAPS_BYTES;
+#pragma unroll
+      for (int k = 0; k < (HALO_PX + 31) / 32; ++k) {
+        const int hp = lane + 32 * k;
+        if (hp < HALO_PX) {
+          const int hy = hp / HALO_W, hx = hp - hy * HALO_W;
+          const unsigned short* wp = reinterpret_cast<const unsigned short*>(win) + hy * SSM_WIN_W + hx;
+          uint32_t t[9];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) t[q] = wp[(q / 3) * SSM_WIN_W + (q % 3)];
+          sts128(dst + (uint32_t)hp * 16u, t[0] | (t[1] << 16), t[2] | (t[3] << 16), t[4] | (t[5] << 16), t[6] | (t[7] << 16));
+          sts128(dst + (uint32_t)(SSM_TAPS_ROWS * 16 + hp * 16), t[8] | (one << 16), one, 0u, 0u);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_taps_full + 8 * tb);
+    }
+  } else if (warp == 10) {
+    // ---- MMA warp: uniform control flow, one elected lane issues (predicated) ----
+    const uint32_t w1_16 = (sbase + SSM_OFF_W1) >> 4, w2_16 = (sbase + SSM_OFF_W2) >> 4, a16 = (sbase + SSM_OFF_A) >> 4;
+    const uint32_t n16 = (uint32_t)p.n_blk;
+    unsigned long long dacc[4] = {0, 0, 0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    auto issue_mlp = [&](int it) {
+      const int tb = it & 1;
+      if (lane == 0) {
+        mbar_wait(bar_taps_full + 8 * tb, ((uint32_t)it >> 1) & 1u);
+        mbar_wait(bar_mlp_empty, ((uint32_t)it & 1u) ^ 1u);           // the converters have drained the previous tile's m1 accumulator
+      }
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t leader = elect_one_sync() ? 1u : 0u;
+      const uint32_t t16 = (sbase + SSM_OFF_TAPS + (uint32_t)tb * SSM_TAPS_BYTES) >> 4;
+      const uint64_t bdesc = desc_noswz(w1_16, SSM_K, 8);
+      umma_f16_pred(tmem_base + SSM_TMEM_MLP, desc_noswz(t16, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u, leader);
+      umma_f16_pred(tmem_base + SSM_TMEM_MLP + SSM_K, desc_noswz(t16 + 128, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u, leader);
+      umma_commit_pred(bar_taps_empty + 8 * tb, leader);
+      umma_commit_pred(bar_mlp_full, leader);
+      __syncwarp();
+    };
+    if (n_my > 0) issue_mlp(0);
+    ITG_SACC(0, tl);
+    for (int it = 0; it < n_my; ++it) {
+      const int b = it & 1;
+      if (lane == 0) mbar_wait(bar_acc_empty + 8 * b, (((uint32_t)it >> 1) & 1u) ^ 1u);
+      __syncwarp();
+      ITG_SACC(1, tl);
+      const uint32_t d = tmem_base + (uint32_t)b * n16;
+      for (int ks = 0; ks < SSM_KSTEPS; ++ks) {
+        if (lane == 0) mbar_wait(bar_a_full + 8 * ks, (uint32_t)it & 1u);
+        __syncwarp();
+        ITG_SACC(2, tl);
+        tc_fence_after();
+        {
+          const uint32_t leader = elect_one_sync() ? 1u : 0u;
+          const uint32_t ak = a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16);
+          const uint32_t wk = w2_16 + (uint32_t)(2 * ks) * n16;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t shift16 = (uint32_t)((t / 3) * HALO_W + (t % 3));
+            umma_f16_pred(d, desc_noswz(ak + shift16, PLANE_BYTES / 16, HALO_W), desc_noswz(wk + (uint32_t)(t * SSM_KG) * n16, n16, 8),
+                          p.idesc_emb, (ks > 0 || t > 0) ? 1u : 0u, leader);
+          }
+          umma_commit_pred(bar_a_empty + 8 * ks, leader);               // the plane pair may be overwritten with the next tile's values
+        }
+        __syncwarp();
+        ITG_SACC(3, tl);
+        if (ks == 2 && it + 1 < n_my) { issue_mlp(it + 1); ITG_SACC(0, tl); }     // 27 embed MMAs are queued while this waits for the converters
+      }
+      umma_commit_pred(bar_acc_full + 8 * b, elect_one_sync() ? 1u : 0u);
+      __syncwarp();
+    }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[i] = dacc[i];
+  } else if (warp >= 4) {
+    // ---- converters: m1 accumulator (TMEM) -> ReLU -> operand type -> A planes.  Warps 4-7: halo pixels 0..127, warps 8-9: 128..179 ----
+    const int rb = (warp - 4) >> 2, q = warp & 3;
+    const int hp = rb * 128 + q * 32 + lane;
+    const bool hp_ok = hp < HALO_PX;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(SSM_TMEM_MLP + rb * SSM_K);
+    const uint32_t dst = sbase + SSM_OFF_A + (uint32_t)hp * 16u;
+    unsigned long long dacc[3] = {0, 0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    for (int it = 0; it < n_my; ++it) {
+      if (lane == 0) mbar_wait(bar_mlp_full, (uint32_t)it & 1u);
+      __syncwarp();
+      ITG_SACC(0, tl);
+      tc_fence_after();
+      for (int ks = 0; ks < SSM_KSTEPS; ++ks) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)(16 * ks), v);
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack2<T>(fmaxf(v[2 * i], 0.f), fmaxf(v[2 * i + 1], 0.f));
+        if (lane == 0) mbar_wait(bar_a_empty + 8 * ks, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's MMAs have read this plane pair
+        __syncwarp();
+        ITG_SACC(1, tl);
+        if (hp_ok) {
+          sts128(dst + (uint32_t)((2 * ks) * PLANE_BYTES), w[0], w[1], w[2], w[3]);
+          sts128(dst + (uint32_t)((2 * ks + 1) * PLANE_BYTES), w[4], w[5], w[6], w[7]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * ks);
+        ITG_SACC(2, tl);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_mlp_empty);
+    }
+    if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) for (int i = 0; i < 3; ++i) p.dbg[4 + i] = dacc[i];
+  } else {
+    // ---- epilogue: embed accumulator -> (1 + gamma) * bn0(x) + beta -> activation -> framed store ----
+    const int row = warp * 32 + lane;
+    unsigned long long dacc[2] = {0, 0};
+    long long tl = p.dbg ? clock64() : 0;
+    int tile = slot;
+    for (int it = 0; it < n_my; ++it, tile += nslots) {
+      const int b = it & 1;
+      const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+      const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
+      const bool valid = (y < p.h) && (x < p.w);
+      if (lane == 0) mbar_wait(bar_acc_full + 8 * b, ((uint32_t)it >> 1) & 1u);
+      __syncwarp();
+      ITG_SACC(0, tl);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.n_blk);
+      for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
+        const int n = nb * p.n_blk + c0;
+        if (n >= p.n_pad) break;
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
+        if (valid) epilogue_ssm16<T>(p.ep, y, x, n, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * b);
+      ITG_SACC(1, tl);
+    }
+    if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0) for (int i = 0; i < 2; ++i) p.dbg[8 + i] = dacc[i];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 11) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace itg

@@ -19,6 +19,7 @@ sub-image protocol (models/layers.py:103-143) and the row-band multi-GPU split p
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -27,14 +28,14 @@ import torch
 from . import _lib as L
 from . import packing as PK
 from .config import GenConfig
-from .ops import AttentionOp, ConvOp, Grid, c_store
+from .ops import AttentionOp, ConvOp, Grid, SsmOp, c_store
 
 PRECISIONS = {
     # name: (torch dtype, conv implementation)
     "fp32": (torch.float32, L.IMPL_DIRECT),     # exact mode: CUDA-core fp32 (the <= 1e-3 gate)
     "fp16": (torch.float16, L.IMPL_AUTO),       # tcgen05 kind::f16, fp16 operands / fp32 accumulate
     "bf16": (torch.bfloat16, L.IMPL_AUTO),      # tcgen05 kind::f16, bf16 operands / fp32 accumulate
-    "fp16-stream": (torch.float16, L.IMPL_UMMA),     # force the per-tap streaming kernel everywhere (A/B comparison)
+    "fp16-stream": (torch.float16, L.IMPL_UMMA),     # force the per-tap streaming kernel everywhere, SSM as two launches (A/B comparison)
     "fp16-direct": (torch.float16, L.IMPL_DIRECT),   # on-device cross-check of the tcgen05 kernel
     "bf16-direct": (torch.bfloat16, L.IMPL_DIRECT),
 }
@@ -80,6 +81,8 @@ class PackedWeights:
             w1 = sd[prefix + "mlp_shared.0.weight"].float().reshape(1, SSM_HIDDEN, 9)      # (128,1,3,3) -> taps as K
             put(prefix + "mlp.w", PK._pad_nk(w1, SSM_HIDDEN, 16).to(dtype))
             put(prefix + "mlp.b", PK.pad_vec(sd[prefix + "mlp_shared.0.bias"], SSM_HIDDEN))
+            if dtype != torch.float32:          # operand of the fused kernel (itg_ssm_fwd): taps + bias hi/lo in one K = 16 row
+                put(prefix + "mlp.wf", PK.pack_ssm_mlp(sd[prefix + "mlp_shared.0.weight"], sd[prefix + "mlp_shared.0.bias"], dtype))
             we, be = PK.pack_ssm_embed(sd[prefix + "embed.weight"], sd[prefix + "embed.bias"], dtype)
             put(prefix + "embed.w", we)
             put(prefix + "embed.b", be)
@@ -150,12 +153,17 @@ class Plan:
     """The launch list of one Generator forward on a th x tw patch grid, with its buffers."""
 
     def __init__(self, cfg: GenConfig, weights: PackedWeights, backend, th: int, tw: int, device,
-                 impl: int, img_layout: int = L.IMG_MERGED, reuse_buffers: bool = True):
+                 impl: int, img_layout: int = L.IMG_MERGED, reuse_buffers: bool = True, fuse_ssm: Optional[bool] = None):
         if th < 1 or tw < 1:
             raise ValueError("patch grid must be at least 1 x 1")
         self.cfg, self.w, self.backend = cfg, weights, backend
         self.th, self.tw, self.device, self.impl = th, tw, device, impl
         self.dtype = weights.dtype
+        # SSM norms as ONE launch each (itg_ssm_fwd, hidden map kept on chip) on the 16-bit tcgen05 path; the fp32 exact mode
+        # and the forced-implementation precisions run mlp_shared and embed as two itg_conv_fwd launches
+        if fuse_ssm is None:
+            fuse_ssm = impl == L.IMPL_AUTO and self.dtype != torch.float32 and not os.environ.get("ITG_SSM_UNFUSED")
+        self.fuse_ssm = bool(fuse_ssm) and cfg.type_norm == "SSM"
         self.img_layout = img_layout
         self.border = L.BORDER_REPLICATE if cfg.border_is_replicate else L.BORDER_CONSTANT
         self._vgrids: List[_VGrid] = []
@@ -288,9 +296,14 @@ class Plan:
             h_raw, a = h_new, a_new
         return a
 
-    def _ssm_norm(self, prefix: str, taps: _VGrid, x: _VGrid, x_shift: int, out: _VGrid, linear: bool, border: int):
+    def _ssm_norm(self, prefix: str, taps: Optional[_VGrid], x: _VGrid, x_shift: int, out: _VGrid, linear: bool, border: int,
+                  level: int = 0):
         """out = [act]((1 + gamma) * bn0(x) + beta) with [gamma|beta] = embed(relu(mlp_shared(map)))."""
         H, W = out.h, out.w
+        if self.fuse_ssm:
+            self._touch(x, out)
+            self._steps.append(("ssm", dict(prefix=prefix, level=level, x=x, x_shift=x_shift, out=out, linear=linear, border=border)))
+            return
         m1 = self._g(f"m1.{prefix}", H + 2, W + 2, SSM_HIDDEN)
         self._conv(prefix + "mlp", L.CONV1X1, taps, prefix + "mlp.", k=16, out_act=m1, leak=0.0, border=L.BORDER_NONE)
         self._conv(prefix + "embed", L.CONV3X3, m1, prefix + "embed.", k=SSM_HIDDEN, out_act=out, linear=linear,
@@ -310,20 +323,22 @@ class Plan:
             last = k == n
             p = f"block{k}."
             x_shift = 0 if k == 1 else 1
-            taps = self._g(f"taps{k}", H + 2, W + 2, 16)
-            self._touch(taps)
-            self._steps.append(("pack_map", (k - 1, taps)))
+            taps = None
+            if not self.fuse_ssm:
+                taps = self._g(f"taps{k}", H + 2, W + 2, 16)
+                self._touch(taps)
+                self._steps.append(("pack_map", (k - 1, taps)))
             a1 = self._g(f"a.{p}conv1", H, W, c_store(ci))
-            self._ssm_norm(p + "bn1.", taps, h_raw, x_shift, a1, False, self.border)
+            self._ssm_norm(p + "bn1.", taps, h_raw, x_shift, a1, False, self.border, k - 1)
             self._halo(p + "conv1", a1, r)
             t = self._g(f"t.{p}", H, W, c_store(co))
             self._conv(p + "conv1", L.CONV3X3, a1, p + "conv1.conv.", out_raw=t)
             a2 = self._g(f"a.{p}conv2", H, W, c_store(co))
-            self._ssm_norm(p + "bn2.", taps, t, 0, a2, False, self.border)
+            self._ssm_norm(p + "bn2.", taps, t, 0, a2, False, self.border, k - 1)
             self._halo(p + "conv2", a2, r)
             if ci != co:
                 s_in = self._g(f"sin.{p}", H, W, c_store(ci))
-                self._ssm_norm(p + "bn3.", taps, h_raw, x_shift, s_in, True, L.BORDER_NONE)
+                self._ssm_norm(p + "bn3.", taps, h_raw, x_shift, s_in, True, L.BORDER_NONE, k - 1)
                 s = self._g(f"s.{p}", H, W, c_store(co))
                 self._conv(p + "conv3", L.CONV1X1, s_in, p + "conv3.", out_raw=s)
                 res, res_shift = s, 0
@@ -402,6 +417,13 @@ class Plan:
                 op = self._attention_op(a)
                 self.ops.append(("att", op))
                 self.fns.append(be.compile_attention(op))
+            elif kind == "ssm":
+                pre = a["prefix"]
+                op = SsmOp(map=self.maps_in[a["level"]], w_mlp=w[pre + "mlp.wf"], w_embed=w[pre + "embed.w"], b_embed=w[pre + "embed.b"],
+                           x=a["x"].grid, x_shift=a["x_shift"], mean=w[pre + "mean"], rstd=w[pre + "rstd"], out=a["out"].grid,
+                           leak=self.cfg.leak, linear=a["linear"], border=a["border"], name=pre + "ssm")
+                self.ops.append(("ssm", op))
+                self.fns.append(be.compile_ssm(op))
             else:
                 op = self._conv_op(a)
                 self.ops.append(("conv", op))

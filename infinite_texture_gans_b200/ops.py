@@ -137,6 +137,24 @@ class AttentionOp:
     name: str = "attention"
 
 
+@dataclass
+class SsmOp:
+    """One itg_ssm_fwd launch (StochasticSpatialModulation.forward, models/layers.py:228-234); mirror of itg_ssm_desc."""
+    map: torch.Tensor                  # fp32 (h+4, w+4) noise map of the level
+    w_mlp: torch.Tensor                # [128, 16] packing.pack_ssm_mlp
+    w_embed: torch.Tensor              # [9, n_pad, 128] packing.pack_ssm_embed
+    b_embed: torch.Tensor              # [n_pad] fp32
+    x: Grid                            # tensor to modulate
+    x_shift: int
+    mean: torch.Tensor
+    rstd: torch.Tensor
+    out: Grid
+    leak: float = 0.0
+    linear: bool = False
+    border: int = L.BORDER_NONE
+    name: str = "ssm"
+
+
 class CudaBackend:
     """Executes ops through libitg_b200.so on the current CUDA stream.  The only backend of the package."""
 
@@ -186,6 +204,35 @@ class CudaBackend:
 
     def conv(self, op: ConvOp) -> None:
         self.compile_conv(op)()
+
+    # ---- SSM ----
+    def compile_ssm(self, op: SsmOp):
+        d = L.SsmDesc()
+        out = op.out
+        if op.map.dtype != torch.float32 or op.map.dim() != 2 or op.map.stride(1) != 1:
+            raise L.ItgError(f"ssm {op.name}: the noise map must be a 2-D fp32 tensor with unit column stride")
+        if tuple(op.map.shape) != (out.h + 4, out.w + 4):
+            raise L.ItgError(f"ssm {op.name}: map {tuple(op.map.shape)} does not match the {out.h}x{out.w} output (+4)")
+        if op.w_mlp.dtype != out.buf.dtype or op.w_embed.dtype != out.buf.dtype or op.x.buf.dtype != out.buf.dtype:
+            raise L.ItgError(f"ssm {op.name}: weights and tensors must share one 16-bit dtype")
+        if tuple(op.w_mlp.shape) != (128, 16) or op.w_embed.shape[0] != 9 or op.w_embed.shape[2] != 128 or not op.w_embed.is_contiguous():
+            raise L.ItgError(f"ssm {op.name}: weight layouts must be [128,16] and [9,n_pad,128]")
+        d.dtype, d.border, d.h, d.w, d.c, d.n_pad = L.DTYPE_OF[out.buf.dtype], op.border, out.h, out.w, out.c, op.w_embed.shape[1]
+        d.map, d.map_pitch, d.x_shift = L.ptr(op.map), op.map.stride(0), op.x_shift
+        d.w_mlp, d.w_embed, d.b_embed = L.ptr(op.w_mlp), L.ptr(op.w_embed), L.ptr(op.b_embed)
+        d.x, d.x_c, d.x_h, d.x_w, d.linear = L.ptr(op.x.buf), op.x.c, op.x.h, op.x.w, int(op.linear)
+        d.mean, d.rstd, d.out, d.leak = L.ptr(op.mean), L.ptr(op.rstd), L.ptr(out.buf), float(op.leak)
+        fn, name = self.lib.itg_ssm_fwd, op.name
+
+        def launch():
+            rc = fn(d, L.stream_ptr())
+            if rc != 0:
+                raise L.ItgError(f"ssm {name}: libitg_b200 error {rc}: {self.lib.itg_last_error().decode()}")
+            self.launches += 1
+        return launch
+
+    def ssm(self, op: SsmOp) -> None:
+        self.compile_ssm(op)()
 
     # ---- attention ----
     def compile_attention(self, op: AttentionOp):

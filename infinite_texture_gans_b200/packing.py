@@ -96,3 +96,18 @@ def pack_ssm_embed(weight: torch.Tensor, bias: torch.Tensor, dtype) -> Tuple[tor
     b[1:2 * C:2] = bias[C:].float()
     n_pad = n_pad_of(2 * cs)
     return pack_conv3x3(w, dtype, n_pad=n_pad), pad_vec(b, n_pad)
+
+
+def pack_ssm_mlp(weight: torch.Tensor, bias: torch.Tensor, dtype) -> torch.Tensor:
+    """SSM `mlp_shared` conv (128, 1, 3, 3) + bias -> the [128, 16] K-major operand of itg_ssm_fwd: columns 0..8 are the taps
+    (ky*3+kx), columns 9 and 10 carry the bias as a 16-bit hi + lo pair (the kernel multiplies them by constant ones, so the
+    fp32 accumulator receives the bias to ~2^-22 relative), the rest is zero (layers.py:220-222, 229)."""
+    n = weight.shape[0]
+    if tuple(weight.shape[1:]) != (1, 3, 3):
+        raise ValueError("the fused SSM kernel serves map_dim = 1 (test_sample.py:56 passes map_dim=1)")
+    out = torch.zeros(n, 16, dtype=torch.float32, device=weight.device)
+    out[:, :9] = weight.float().reshape(n, 9)
+    hi = bias.float().to(dtype).float()
+    out[:, 9] = hi
+    out[:, 10] = (bias.float() - hi).to(dtype).float()
+    return out.to(dtype).contiguous()

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from infinite_texture_gans_b200 import _lib as L
-from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid
+from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid, SsmOp
 
 
 def _act(v, leak):
@@ -138,6 +138,29 @@ class EmulatorBackend:
 
     def compile_conv(self, op: ConvOp):
         return lambda: self.conv(op)
+
+    # ---- SSM (itg_ssm_fwd) ----
+    def ssm(self, op: SsmOp) -> None:
+        """m1 = relu(conv3x3_valid(map rounded to the operand type) + bias), rounded to the operand type; embed conv + modulation in fp32."""
+        self.launches += 1
+        dt = op.out.buf.dtype
+        H, W, C = op.out.h, op.out.w, op.out.c
+        m = op.map.to(dt).float()                                           # (H+4, W+4)
+        w1 = op.w_mlp.float()                                               # [128, 16]
+        taps = torch.stack([m[t // 3:t // 3 + H + 2, t % 3:t % 3 + W + 2] for t in range(9)], -1)      # (H+2, W+2, 9)
+        m1 = torch.relu(taps @ w1[:, :9].t() + (w1[:, 9] + w1[:, 10])).to(dt).float()                    # (H+2, W+2, 128)
+        we = op.w_embed.float()                                             # [9, n_pad, 128]
+        v = sum(m1[t // 3:t // 3 + H, t % 3:t % 3 + W] @ we[t].t() for t in range(9)) + op.b_embed.float()
+        gamma, beta = v[..., 0:2 * C:2], v[..., 1:2 * C:2]
+        xm = _up(op.x.interior[..., :C].float(), op.x_shift, H, W)
+        y = (1 + gamma) * ((xm - op.mean.float()[:C]) * op.rstd.float()[:C]) + beta
+        if not op.linear:
+            y = _act(y, op.leak)
+        op.out.interior.copy_(y.to(dt))
+        _fill_frame_fast(op.out.buf, op.border)
+
+    def compile_ssm(self, op: SsmOp):
+        return lambda: self.ssm(op)
 
     # ---- attention (itg_attention_fwd) ----
     def attention(self, op: AttentionOp) -> None:

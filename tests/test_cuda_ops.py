@@ -13,7 +13,7 @@ import torch
 from emulator import EmulatorBackend
 from infinite_texture_gans_b200 import _lib as L
 from infinite_texture_gans_b200 import packing as PK
-from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid, c_store
+from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid, SsmOp, c_store
 
 pytestmark = pytest.mark.gpu
 
@@ -199,6 +199,55 @@ def test_ssm_embed_conv_matches_emulator(be, precision, impl, C, shift, linear):
     opg = _run_both(be, op, _conv_to_dev)
     a, r = (opg.out_act.interior, op.out_act.interior) if linear else (opg.out_act.buf, op.out_act.buf)
     _cmp(op.name, a, r, dtype)
+
+
+SSM_CASES = [
+    # (C, H, W, x_shift, linear, border): N = 2 * c_store(C) GEMM columns -> ceil(N / 64) resident column blocks
+    (26, 22, 36, 0, False, L.BORDER_REPLICATE),        # one block, partial tiles on both edges
+    (52, 22, 36, 1, False, L.BORDER_REPLICATE),        # two blocks (64 + 48 columns)
+    (104, 40, 24, 1, True, L.BORDER_NONE),             # four blocks, the shortcut's bn3 (no activation, frame left to the caller)
+    (8, 9, 13, 0, False, L.BORDER_CONSTANT),           # 16 columns, a single partial tile row
+    (416, 12, 20, 0, False, L.BORDER_REPLICATE),       # 13 blocks, fewer tiles than SMs per block
+    (26, 320, 328, 0, False, L.BORDER_REPLICATE),      # 820 tiles: 5-6 per CTA, every mbarrier wraps its phase several times
+    (52, 200, 264, 1, False, L.BORDER_CONSTANT),       # two blocks x 6 tiles per CTA
+]
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", SSM_CASES, ids=lambda c: f"C{c[0]}_{c[1]}x{c[2]}_s{c[3]}")
+def test_fused_ssm_matches_emulator(be, precision, case):
+    """itg_ssm_fwd (mlp_shared -> ReLU -> embed -> modulation in one launch, hidden map on chip; layers.py:228-234) against the
+    CPU emulation of the same descriptor on identical operands."""
+    C, H, W, shift, linear, border = case
+    dtype = DT[precision]
+    g = torch.Generator().manual_seed(C * 13 + H + shift)
+    cs = c_store(C)
+    w_mlp = PK.pack_ssm_mlp(torch.randn(128, 1, 3, 3, generator=g) / 3.0, 0.2 * torch.randn(128, generator=g), dtype)
+    w_emb, b_emb = PK.pack_ssm_embed(torch.randn(2 * C, 128, 3, 3, generator=g) / math.sqrt(9 * 128), 0.1 * torch.randn(2 * C, generator=g), dtype)
+    xh, xw = (H + shift) >> shift, (W + shift) >> shift
+    x = _grid(xh, xw, cs, dtype, g)
+    x.buf[..., C:] = 0
+    mk = lambda dev: SsmOp(
+        map=torch.randn(H + 4, W + 4, generator=torch.Generator().manual_seed(H * W)).to(dev), w_mlp=w_mlp.to(dev), w_embed=w_emb.to(dev),
+        b_embed=b_emb.to(dev), x=Grid(x.buf.clone().to(dev), xh, xw, cs), x_shift=shift,
+        mean=PK.pad_vec(0.1 * torch.randn(C, generator=torch.Generator().manual_seed(1)), cs).to(dev),
+        rstd=PK.pad_vec(1 + 0.2 * torch.rand(C, generator=torch.Generator().manual_seed(2)), cs).to(dev),
+        out=Grid(torch.full((H + 2, W + 2, cs), 7.0).to(dtype).to(dev), H, W, cs), leak=0.02, linear=linear, border=border, name=f"ssm{C}")
+    opc, opg = mk("cpu"), mk("cuda")
+    EmulatorBackend().ssm(opc)
+    be.ssm(opg)
+    torch.cuda.synchronize()
+    a, r = (opg.out.interior, opc.out.interior) if border == L.BORDER_NONE else (opg.out.buf, opc.out.buf)
+    # the hidden map is rounded to the operand type on both sides; a rounding flip there (bias carried as hi + lo) moves one of the
+    # 1152 products by one ulp: allow 2x the single-rounding budget
+    got, ref = a.float().cpu(), r.float()
+    scale = max(ref.abs().max().item(), 1e-6)
+    err = (got - ref).abs().max().item()
+    assert err <= 2 * REL[dtype] * scale + 1e-6, f"ssm C={C}: max-abs {err:.3e} at output scale {scale:.3e}"
+    with pytest.raises(L.ItgError):
+        bad = mk("cuda")
+        bad.map = bad.map[:, :-1].contiguous()
+        be.ssm(bad)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])

@@ -52,6 +52,29 @@ def test_reference_style_map_crops_are_accepted():
     compare_with_golden(d, "one", itg.utils.merge_patches_into_image(patches, th, tw), 5e-5)
 
 
+def test_fused_ssm_plan_matches_reference():
+    """16-bit plans run every StochasticSpatialModulation as ONE itg_ssm_fwd launch (hidden map on chip): the launch list has no
+    tap-stack / mlp / embed launches, needs a fraction of the two-launch plan's memory, and (emulated) still reproduces the reference."""
+    from infinite_texture_gans_b200.engine import Engine, Plan
+    d, kw, ocfg, sd, z, maps = load_case("gen_ssm4_att_rep")
+    th, tw = int(d["total_h"]), int(d["total_w"])
+    eng = Engine(GenConfig(**kw), sd, "fp16", "cpu", backend=EmulatorBackend())
+    fused = Plan(eng.cfg, eng.weights, eng.backend, th, tw, eng.device, eng.impl)
+    split = Plan(eng.cfg, eng.weights, eng.backend, th, tw, eng.device, eng.impl, fuse_ssm=False)
+    kinds = [k for k, _ in fused.ops]
+    n_norms = sum(3 if ci != co else 2 for ci, co in eng.cfg.block_channels())
+    assert fused.fuse_ssm and kinds.count("ssm") == n_norms and "pack_map" not in kinds
+    assert [k for k, _ in split.ops].count("pack_map") == eng.cfg.n_layers_G
+    assert fused.n_launches == split.n_launches - n_norms - eng.cfg.n_layers_G
+    assert fused.arena_bytes < 0.5 * split.arena_bytes
+    outs = []
+    for p in (fused, split):
+        p.set_inputs(z, [m[0, 0] for m in maps])
+        outs.append(p.run().clone())
+        compare_with_golden(d, "one", outs[-1], 2e-2)
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-2     # same arithmetic up to the bias's hi + lo split; rounding flips of the 16-bit hidden map propagate
+
+
 def test_inter_location_without_state_raises():
     d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
     net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
@@ -120,8 +143,9 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), s
     lib2 = L.load()
-    assert lib2.itg_version() == 1
+    assert lib2.itg_version() == 2
     assert lib2.itg_conv_desc_size() == ctypes.sizeof(L.ConvDesc)
+    assert lib2.itg_ssm_desc_size() == ctypes.sizeof(L.SsmDesc)
 
 
 def test_missing_library_fails_loudly(monkeypatch):
