@@ -238,7 +238,7 @@ int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int3
  * same arithmetic (same fp32 operations in the same order, no FMA contraction: bit-identical bytes) on the device, so
  * that 1 byte instead of 4 crosses PCIe per sample.  img: planar fp32 (c, h, w) with `row_pitch` floats between rows
  * and `plane_pitch` floats between channels (a cropped view of the Generator's output buffer); out: interleaved
- * (h, w, c) uint8, contiguous -- the layout PIL / image encoders take.  c <= 4. */
+ * (h, w, c) uint8, contiguous -- the layout PIL / image encoders take.  c <= 8 (the Generator's img_ch range). */
 int itg_image_to_u8(const float* img, int32_t c, int32_t h, int32_t w, int64_t row_pitch, int64_t plane_pitch,
                     uint8_t* out, void* stream);
 

@@ -8,11 +8,13 @@
 #include <cstdlib>
 
 #include "attention.cuh"
+#include "data_movement.cuh"
 #include "attention_mma.cuh"
 #include "conv_direct.cuh"
 #include "conv_umma.cuh"
 #include "conv_tile.cuh"
 #include "ssm_fused.cuh"
+#include "ssm_fused2.cuh"
 
 namespace {
 
@@ -458,7 +460,8 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
-// StochasticSpatialModulation as one launch (ssm_fused.cuh)
+// StochasticSpatialModulation as one launch: CTA pairs with tcgen05.mma.cta_group::2 (ssm_fused2.cuh), or single CTAs (ssm_fused.cuh;
+// ITG_SSM_CG=1, and whenever the pair kernel cannot serve the shape)
 template <typename T>
 int launch_ssm(const itg_ssm_desc& d, cudaStream_t st) {
   itg::SsmParams p;
@@ -469,17 +472,35 @@ int launch_ssm(const itg_ssm_desc& d, cudaStream_t st) {
   p.map = d.map; p.map_pitch = d.map_pitch;
   p.w1 = d.w_mlp; p.w2 = d.w_embed;
   p.n_pad = d.n_pad;
-  // N blocking: the weights of one block (all taps, K = 128) stay in shared memory for the whole launch
-  p.nblocks = (d.n_pad + itg::SSM_NBLK_MAX - 1) / itg::SSM_NBLK_MAX;
-  p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 15) / 16 * 16;
   const int sms = sm_count();
-  if (p.nblocks > sms) return fail(ITG_ERR_UNSUPPORTED, "ssm: %d GEMM columns need more column blocks than there are SMs", d.n_pad);
-  int nslots = sms / p.nblocks;
-  if (nslots > p.ntiles) nslots = p.ntiles;
-  const int grid = nslots * p.nblocks;
+  static const int env_cg = getenv("ITG_SSM_CG") ? atoi(getenv("ITG_SSM_CG")) : 2;
+  int cg = env_cg == 1 ? 1 : 2;
+  // N blocking: the weights of one block (all taps, K = 128) stay in shared memory for the whole launch -- 64 columns per CTA
+  if (cg == 2) {
+    p.nblocks = (d.n_pad + itg::SSM2_NPAIR_MAX - 1) / itg::SSM2_NPAIR_MAX;
+    p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 31) / 32 * 32;            // per pair; each CTA parks n_blk / 2 columns
+    if (p.nblocks > sms / 2) cg = 1;
+  }
+  if (cg == 1) {
+    p.nblocks = (d.n_pad + itg::SSM_NBLK_MAX - 1) / itg::SSM_NBLK_MAX;
+    p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 15) / 16 * 16;
+    if (p.nblocks > sms) return fail(ITG_ERR_UNSUPPORTED, "ssm: %d GEMM columns need more column blocks than there are SMs", d.n_pad);
+  }
+  int grid;
+  if (cg == 2) {
+    int nslots = (sms / 2) / p.nblocks;
+    const int npt = (p.ntiles + 1) / 2;
+    if (nslots > npt) nslots = npt;
+    grid = 2 * nslots * p.nblocks;
+  } else {
+    int nslots = sms / p.nblocks;
+    if (nslots > p.ntiles) nslots = p.ntiles;
+    grid = nslots * p.nblocks;
+  }
   const uint32_t fmt = (d.dtype == ITG_BF16) ? 1u : 0u;
-  p.idesc_mlp = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(itg::SSM_K >> 3) << 17) | ((128u >> 4) << 24);
-  p.idesc_emb = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_blk >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t m_enc = (cg == 2 ? 256u : 128u) >> 4;
+  p.idesc_mlp = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(itg::SSM_K >> 3) << 17) | (m_enc << 24);
+  p.idesc_emb = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_blk >> 3) << 17) | (m_enc << 24);
   itg::EpiParams& ep = p.ep;
   ep.out_h = d.h; ep.out_w = d.w; ep.out_c = d.c; ep.n_pad = d.n_pad;
   ep.bias = d.b_embed;
@@ -493,21 +514,28 @@ int launch_ssm(const itg_ssm_desc& d, cudaStream_t st) {
     ITG_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st));
     p.dbg = dbg_buf;
   }
-  const int smem = itg::ssm_smem_bytes(p.n_blk);
-  static bool attr_set[MAX_DEVICES] = {false};
+  static bool attr_set[MAX_DEVICES][2] = {{false, false}};
   const int dev = current_device();
-  if (!attr_set[dev]) {
-    ITG_CUDA(cudaFuncSetAttribute(itg::ssm_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[dev] = true;
+  if (cg == 2) {
+    if (!attr_set[dev][1]) {
+      ITG_CUDA(cudaFuncSetAttribute(itg::ssm_fused2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set[dev][1] = true;
+    }
+    ITG_CUDA(launch_pdl_cluster(itg::ssm_fused2_kernel<T>, dim3(grid), dim3(itg::SSM_THREADS), itg::ssm2_smem_bytes(p.n_blk / 2), st, 2, p));
+  } else {
+    if (!attr_set[dev][0]) {
+      ITG_CUDA(cudaFuncSetAttribute(itg::ssm_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set[dev][0] = true;
+    }
+    ITG_CUDA(launch_pdl(itg::ssm_fused_kernel<T>, dim3(grid), dim3(itg::SSM_THREADS), itg::ssm_smem_bytes(p.n_blk), st, p));
   }
-  ITG_CUDA(launch_pdl(itg::ssm_fused_kernel<T>, dim3(grid), dim3(itg::SSM_THREADS), smem, st, p));
   if (dbg_on) {
     unsigned long long hst[16];
     ITG_CUDA(cudaStreamSynchronize(st));
     ITG_CUDA(cudaMemcpy(hst, dbg_buf, sizeof(hst), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[itg ssm dbg] %dx%d n_pad=%d n_blk=%d nblocks=%d tiles=%d grid=%d | kcycles CTA0: mma.mlp=%.1f mma.wait_acc=%.1f mma.wait_a=%.1f mma.issue=%.1f "
+    fprintf(stderr, "[itg ssm dbg] cg%d %dx%d n_pad=%d n_blk=%d nblocks=%d tiles=%d grid=%d | kcycles CTA0: mma.mlp=%.1f mma.wait_acc=%.1f mma.wait_a=%.1f mma.issue=%.1f "
             "cvt.wait_mlp=%.1f cvt.wait_a_empty=%.1f cvt.work=%.1f epi.wait=%.1f epi.work=%.1f\n",
-            d.h, d.w, d.n_pad, p.n_blk, p.nblocks, p.ntiles, grid, hst[0] / 1e3, hst[1] / 1e3, hst[2] / 1e3, hst[3] / 1e3, hst[4] / 1e3,
+            cg, d.h, d.w, d.n_pad, p.n_blk, p.nblocks, p.ntiles, grid, hst[0] / 1e3, hst[1] / 1e3, hst[2] / 1e3, hst[3] / 1e3, hst[4] / 1e3,
             hst[5] / 1e3, hst[6] / 1e3, hst[8] / 1e3, hst[9] / 1e3);
   }
   ITG_CUDA(cudaGetLastError());
@@ -701,6 +729,10 @@ int itg_halo_exchange(int32_t dtype, void* grid, int32_t h, int32_t w, int32_t c
   p.grid = grid; p.h = h; p.w = w; p.c = c;
   p.up_inbox = up_inbox; p.down_inbox = down_inbox; p.up_flag = up_flag; p.down_flag = down_flag;
   p.top_inbox = top_inbox; p.bot_inbox = bot_inbox; p.top_flag = top_flag; p.bot_flag = bot_flag; p.step = step; p.roles = roles;
+  // ranks drift (lazy plan / graph builds, first-use module loads, GC or IO stalls on one rank): wait a minute before declaring the
+  // neighbour dead.  ITG_HALO_TIMEOUT_S overrides; P2PBandHalo also aligns the ranks with a barrier before the first step.
+  static const long long timeout_s = getenv("ITG_HALO_TIMEOUT_S") ? atoll(getenv("ITG_HALO_TIMEOUT_S")) : 60;
+  p.timeout_cycles = (timeout_s > 0 ? timeout_s : 60) * 2000000000LL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == ITG_F32) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<float>, dim3(4), dim3(1024), 0, st, p));
   else if (dtype == ITG_F16) ITG_CUDA(launch_pdl(itg::halo_xchg_kernel<__half>, dim3(4), dim3(1024), 0, st, p));
@@ -731,7 +763,7 @@ int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int3
 }
 
 int itg_image_to_u8(const float* img, int32_t c, int32_t h, int32_t w, int64_t row_pitch, int64_t plane_pitch, uint8_t* out, void* stream) {
-  if (!img || !out || c < 1 || c > 4 || h < 1 || w < 1 || row_pitch < w || plane_pitch < (int64_t)h * row_pitch - (row_pitch - w))
+  if (!img || !out || c < 1 || c > 8 || h < 1 || w < 1 || row_pitch < w || plane_pitch < (int64_t)h * row_pitch - (row_pitch - w))
     return fail(ITG_ERR_INVALID, "image_to_u8: bad arguments");
   const int blocks = blocks_for((size_t)h * w, 256);
   itg::image_to_u8_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, c, h, w, row_pitch, plane_pitch, out);

@@ -18,8 +18,8 @@
 //      <= 144 KB) are parked in shared memory for the whole launch: in steady state the kernel loads nothing but the
 //      1-channel map, x and its own output.  Wider layers (N = 2C > 64) are split into N blocks over the CTAs
 //      (CTA c serves block c % nblocks; m1 is recomputed per block, which costs two small MMAs and one conversion);
-//   5. four epilogue warps drain the embed accumulator (double-buffered in TMEM) through the modulation epilogue
-//      (epilogue_ssm16, itg_common.cuh) while the next tile is being computed.
+//   5. eight epilogue warps drain the embed accumulator (double-buffered in TMEM) through the modulation epilogue while the
+//      next tile is being computed; x is fetched before they sleep on the MMA barrier, the per-channel vectors sit in shared memory.
 // The plane-pair granularity of step 3/4 lets the conversion of tile i+1 trail the embed MMAs of tile i by one k-step, so
 // one 45 KB A buffer suffices next to the parked weights.  Every mbarrier has one producing and one consuming role that
 // walk its phases in order (see conv_tile.cuh for why that matters).
@@ -31,7 +31,12 @@ namespace itg {
 constexpr int SSM_K = 128;                                   // nhidden of StochasticSpatialModulation (models/layers.py:220)
 constexpr int SSM_KG = SSM_K / 8;                            // 8-channel planes of the A operand
 constexpr int SSM_KSTEPS = SSM_K / 16;
-constexpr int SSM_WARPS = 12;                                // 0-3 epilogue, 4-9 converters, 10 MMA, 11 taps producer + TMEM allocator
+// Warp roles.  A warp's scheduler is warp % 4 and so is the TMEM lane quarter it may read; within a scheduler the hardware favours the
+// HIGHER warp id (measured: with the epilogue warps on top, their barrier polling starved the MMA warp and the converters -- 25 % slower).
+// So the roles that feed the tensor pipe sit on top: 15 MMA issuer, 14 taps producer (+ TMEM allocator), 12-13 converters of halo pixels
+// 128..179, 8-11 converters of halo pixels 0..127, and the two epilogue groups 0-3 / 4-7 at the bottom.
+constexpr int SSM_WARPS = 16;
+constexpr int SSM_WARP_MMA = 15, SSM_WARP_PROD = 14, SSM_WARP_CVT = 8;
 constexpr int SSM_THREADS = 32 * SSM_WARPS;
 constexpr int SSM_NBLK_MAX = 64;                             // GEMM columns whose weights fit shared memory next to the A planes
 constexpr int SSM_TAPS_ROWS = 256;                           // 180 halo pixels padded to two M = 128 row blocks
@@ -39,7 +44,8 @@ constexpr int SSM_TAPS_BYTES = 2 * SSM_TAPS_ROWS * 16;       // two 8-element K 
 constexpr int SSM_W1_BYTES = 2 * SSM_K * 16;
 constexpr int SSM_WIN_W = TILE_W + 4, SSM_WIN_H = TILE_H + 4;   // map window of one tile: 12 x 20
 constexpr int SSM_WIN_N = SSM_WIN_W * SSM_WIN_H;
-constexpr int SSM_HDR = 1024;
+constexpr int SSM_HDR = 1024;                                 // barriers | embed bias (64 floats) | mean (32) | rstd (32) of this CTA's column block
+constexpr int SSM_VEC_BIAS = 256, SSM_VEC_MEAN = 512, SSM_VEC_RSTD = 640;
 constexpr int SSM_OFF_W1 = SSM_HDR;
 constexpr int SSM_OFF_TAPS = SSM_OFF_W1 + SSM_W1_BYTES;                // 2 buffers
 constexpr int SSM_OFF_WIN = SSM_OFF_TAPS + 2 * SSM_TAPS_BYTES;         // 16-bit staging of the map window
@@ -85,7 +91,7 @@ ssm_fused_kernel(const SsmParams p) {
   const uint32_t bar_a_full = sbase + 64;          // [8]  converters (6 warps) -> MMA, one per plane pair
   const uint32_t bar_a_empty = sbase + 128;        // [8]  MMA commit -> converters
   const uint32_t bar_acc_full = sbase + 192;       // [2]  MMA commit -> epilogue
-  const uint32_t bar_acc_empty = sbase + 208;      // [2]  epilogue (4 warps) -> MMA
+  const uint32_t bar_acc_empty = sbase + 208;      // [2]  epilogue (8 warps) -> MMA
   const uint32_t tmem_slot = sbase + 224;
 
   const int nb = (int)blockIdx.x % p.nblocks;      // this CTA's block of GEMM columns (weights resident)
@@ -93,12 +99,12 @@ ssm_fused_kernel(const SsmParams p) {
   const int n_my = slot < p.ntiles ? (p.ntiles - slot + nslots - 1) / nslots : 0;
 
   pdl_launch_dependents();
-  if (warp == 10 && lane == 0) {
+  if (warp == SSM_WARP_MMA && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_taps_full + 8 * i, 32);
       mbar_init(bar_taps_empty + 8 * i, 1);
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);
+      mbar_init(bar_acc_empty + 8 * i, 8);
     }
     mbar_init(bar_mlp_full, 1);
     mbar_init(bar_mlp_empty, 6);
@@ -108,7 +114,7 @@ ssm_fused_kernel(const SsmParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 11) tmem_alloc(tmem_slot, 512);
+  if (warp == SSM_WARP_PROD) tmem_alloc(tmem_slot, 512);
 
   // ---- park the weights (they do not depend on the previous launch): embed block [tap][k-group][n][8 ch], W1 [k-group][n][8 ch] ----
   {
@@ -131,6 +137,16 @@ ssm_fused_kernel(const SsmParams p) {
     for (int i = threadIdx.x; i < 2 * SSM_TAPS_BYTES / 16; i += SSM_THREADS)       // rows 180..255 of the taps operand stay zero
       sts128(sbase + SSM_OFF_TAPS + (uint32_t)i * 16u, 0u, 0u, 0u, 0u);
     fence_proxy_async();                                                           // generic writes -> async proxy (UMMA) reads
+    float* const vec = reinterpret_cast<float*>(sptr);
+    if (threadIdx.x < SSM_NBLK_MAX) {
+      const int n = nb * p.n_blk + (int)threadIdx.x;
+      vec[SSM_VEC_BIAS / 4 + threadIdx.x] = ((int)threadIdx.x < p.n_blk && n < p.n_pad) ? p.ep.bias[n] : 0.f;
+    } else if (threadIdx.x < SSM_NBLK_MAX + SSM_NBLK_MAX / 2) {
+      const int i = (int)threadIdx.x - SSM_NBLK_MAX, ch = ((nb * p.n_blk) >> 1) + i;
+      const bool ok = 2 * i < p.n_blk && ch < p.ep.out_c;
+      vec[SSM_VEC_MEAN / 4 + i] = ok ? p.ep.mod_mean[ch] : 0.f;
+      vec[SSM_VEC_RSTD / 4 + i] = ok ? p.ep.mod_rstd[ch] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -139,7 +155,7 @@ ssm_fused_kernel(const SsmParams p) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();                                       // x (and, in a captured step, the map) of the previous launches are complete from here on
 
-  if (warp == 11) {
+  if (warp == SSM_WARP_PROD) {
     // ---- taps producer: map window -> K = 16 operand rows of the tile's 180 halo pixels ----
     T* const win = reinterpret_cast<T*>(sptr + SSM_OFF_WIN);
     const int map_h = p.h + 4, map_w = p.w + 4;
@@ -180,7 +196,7 @@ ssm_fused_kernel(const SsmParams p) {
       fence_proxy_async();
       mbar_arrive(bar_taps_full + 8 * tb);
     }
-  } else if (warp == 10) {
+  } else if (warp == SSM_WARP_MMA) {
     // ---- MMA warp: uniform control flow, one elected lane issues (predicated) ----
     const uint32_t w1_16 = (sbase + SSM_OFF_W1) >> 4, w2_16 = (sbase + SSM_OFF_W2) >> 4, a16 = (sbase + SSM_OFF_A) >> 4;
     const uint32_t n16 = (uint32_t)p.n_blk;
@@ -236,9 +252,9 @@ ssm_fused_kernel(const SsmParams p) {
       __syncwarp();
     }
     if (p.dbg && blockIdx.x == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[i] = dacc[i];
-  } else if (warp >= 4) {
+  } else if (warp >= SSM_WARP_CVT) {
     // ---- converters: m1 accumulator (TMEM) -> ReLU -> operand type -> A planes.  Warps 4-7: halo pixels 0..127, warps 8-9: 128..179 ----
-    const int rb = (warp - 4) >> 2, q = warp & 3;
+    const int rb = (warp - SSM_WARP_CVT) >> 2, q = warp & 3;
     const int hp = rb * 128 + q * 32 + lane;
     const bool hp_ok = hp < HALO_PX;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(SSM_TMEM_MLP + rb * SSM_K);
@@ -272,10 +288,16 @@ ssm_fused_kernel(const SsmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_mlp_empty);
     }
-    if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) for (int i = 0; i < 3; ++i) p.dbg[4 + i] = dacc[i];
+    if (p.dbg && blockIdx.x == 0 && warp == SSM_WARP_CVT && lane == 0) for (int i = 0; i < 3; ++i) p.dbg[4 + i] = dacc[i];
   } else {
-    // ---- epilogue: embed accumulator -> (1 + gamma) * bn0(x) + beta -> activation -> framed store ----
-    const int row = warp * 32 + lane;
+    // ---- epilogue (two groups of four warps; group g drains the 16-column chunks c = g, g + 2 of every tile):
+    //      embed accumulator -> (1 + gamma) * bn0(x) + beta -> activation -> framed store.  x does not depend on the accumulator: its
+    //      16 bytes per chunk are fetched before sleeping on the MMA barrier; bias / mean / rstd of the column block come from shared memory ----
+    const int eg = warp >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const EpiParams& ep = p.ep;
+    const uint32_t vb = sbase + SSM_VEC_BIAS, vm = sbase + SSM_VEC_MEAN, vr = sbase + SSM_VEC_RSTD;
+    const int n0 = nb * p.n_blk;
     unsigned long long dacc[2] = {0, 0};
     long long tl = p.dbg ? clock64() : 0;
     int tile = slot;
@@ -284,17 +306,50 @@ ssm_fused_kernel(const SsmParams p) {
       const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
       const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
       const bool valid = (y < p.h) && (x < p.w);
+      bool live[2], ok[2];
+      uint4 xr[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = eg + 2 * j, n = n0 + 16 * c;
+        live[j] = 16 * c < p.n_blk && n < p.n_pad;                    // warp-uniform: the chunk exists
+        ok[j] = live[j] && valid && (n >> 1) < ep.out_c;
+        xr[j] = make_uint4(0, 0, 0, 0);
+        if (ok[j])
+          xr[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(ep.mod_x) +
+                                                  grid_off(y >> ep.mod_shift, x >> ep.mod_shift, ep.mod_w, ep.mod_c, n >> 1));
+      }
       if (lane == 0) mbar_wait(bar_acc_full + 8 * b, ((uint32_t)it >> 1) & 1u);
       __syncwarp();
       ITG_SACC(0, tl);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * p.n_blk);
-      for (int c0 = 0; c0 < p.n_blk; c0 += 16) {
-        const int n = nb * p.n_blk + c0;
-        if (n >= p.n_pad) break;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.n_blk);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = eg + 2 * j;
+        if (!live[j]) continue;
         float v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
-        if (valid) epilogue_ssm16<T>(p.ep, y, x, n, v);
+        tmem_ld16(trow + (uint32_t)(16 * c), v);
+        if (!ok[j]) continue;
+        float xf[8], yv[8];
+        {
+          const Vec8<T> t8 = *reinterpret_cast<const Vec8<T>*>(&xr[j]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xf[i] = Op<T>::to_f(t8.v[i]);
+        }
+        const float4 m0 = lds_f4(vm + (uint32_t)(32 * c)), m1 = lds_f4(vm + (uint32_t)(32 * c + 16));
+        const float4 r0 = lds_f4(vr + (uint32_t)(32 * c)), r1 = lds_f4(vr + (uint32_t)(32 * c + 16));
+        const float mean[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const float rstd[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {                                  // 4 columns = (gamma, beta) of two channels
+          const float4 bb = lds_f4(vb + (uint32_t)(64 * c + 16 * h));
+          const float g0 = v[4 * h] + bb.x, b0 = v[4 * h + 1] + bb.y, g1 = v[4 * h + 2] + bb.z, b1 = v[4 * h + 3] + bb.w;
+          const float u0 = (1.f + g0) * ((xf[2 * h] - mean[2 * h]) * rstd[2 * h]) + b0;
+          const float u1 = (1.f + g1) * ((xf[2 * h + 1] - mean[2 * h + 1]) * rstd[2 * h + 1]) + b1;
+          yv[2 * h] = ep.act_linear ? u0 : act_fn(u0, ep.leak);
+          yv[2 * h + 1] = ep.act_linear ? u1 : act_fn(u1, ep.leak);
+        }
+        store8_framed(reinterpret_cast<T*>(ep.out_act), y, x, ep.out_h, ep.out_w, ep.out_c, (n0 + 16 * c) >> 1, yv, ep.border);
       }
       tc_fence_before();
       __syncwarp();
@@ -306,7 +361,7 @@ ssm_fused_kernel(const SsmParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) tmem_dealloc(tmem_base, 512);
+  if (warp == SSM_WARP_PROD) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace itg

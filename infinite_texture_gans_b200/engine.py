@@ -153,7 +153,8 @@ class Plan:
     """The launch list of one Generator forward on a th x tw patch grid, with its buffers."""
 
     def __init__(self, cfg: GenConfig, weights: PackedWeights, backend, th: int, tw: int, device,
-                 impl: int, img_layout: int = L.IMG_MERGED, reuse_buffers: bool = True, fuse_ssm: Optional[bool] = None):
+                 impl: int, img_layout: int = L.IMG_MERGED, reuse_buffers: bool = True, fuse_ssm: Optional[bool] = None,
+                 pre_tanh: bool = False):
         if th < 1 or tw < 1:
             raise ValueError("patch grid must be at least 1 x 1")
         self.cfg, self.w, self.backend = cfg, weights, backend
@@ -164,6 +165,7 @@ class Plan:
         if fuse_ssm is None:
             fuse_ssm = impl == L.IMPL_AUTO and self.dtype != torch.float32 and not os.environ.get("ITG_SSM_UNFUSED")
         self.fuse_ssm = bool(fuse_ssm) and cfg.type_norm == "SSM"
+        self.pre_tanh = pre_tanh      # parity aid: the final conv also leaves its fp32 pre-activation (generators.py:119) in self.out_pre
         self.img_layout = img_layout
         self.border = L.BORDER_REPLICATE if cfg.border_is_replicate else L.BORDER_CONSTANT
         self._vgrids: List[_VGrid] = []
@@ -182,6 +184,7 @@ class Plan:
             self.out = torch.empty((1, cfg.img_ch, th * P, tw * P), dtype=torch.float32, device=device)
         else:
             self.out = torch.empty((th * tw, cfg.img_ch, P, P), dtype=torch.float32, device=device)
+        self.out_pre = torch.empty((th * P, tw * P, 8), dtype=torch.float32, device=device) if pre_tanh else None
         self._build()
         self._materialise(reuse_buffers)
 
@@ -448,8 +451,11 @@ class Plan:
         mh, mw = op.m_h, op.m_w
         op.out_h, op.out_w = a["out_hw"] if a["out_hw"] is not None else (mh, mw)
         if a["img"]:
-            op.out_img, op.img_c, op.img_layout, op.patch = self.out, cfg.img_ch, self.img_layout, cfg.patch_px
             op.out_c = 8
+            if self.pre_tanh:
+                op.out_f32 = self.out_pre
+                return op
+            op.out_img, op.img_c, op.img_layout, op.patch = self.out, cfg.img_ch, self.img_layout, cfg.patch_px
             return op
         outs = [g for g in (a["out_raw"], a["out_act"]) if g is not None]
         op.out_c = a["out_c"] if a["out_c"] is not None else outs[0].c
@@ -533,16 +539,24 @@ class Engine:
             backend = CudaBackend()
         self.backend = backend
         self.weights = PackedWeights(cfg, state_dict, self.dtype, self.device)
-        self._plans: Dict[Tuple[int, int, int], Plan] = {}
+        self._plans: Dict[Tuple[int, int, int, bool], Plan] = {}
         self._graphs: Dict[Tuple[int, int, int], "torch.cuda.CUDAGraph"] = {}
 
-    def plan(self, th: int, tw: int, img_layout: int = L.IMG_MERGED) -> Plan:
-        key = (th, tw, img_layout)
+    def plan(self, th: int, tw: int, img_layout: int = L.IMG_MERGED, pre_tanh: bool = False) -> Plan:
+        key = (th, tw, img_layout, pre_tanh)
         p = self._plans.get(key)
         if p is None:
-            p = Plan(self.cfg, self.weights, self.backend, th, tw, self.device, self.impl, img_layout)
+            p = Plan(self.cfg, self.weights, self.backend, th, tw, self.device, self.impl, img_layout, pre_tanh=pre_tanh)
             self._plans[key] = p
         return p
+
+    def forward_pre_tanh(self, z: torch.Tensor, maps: Optional[Sequence[torch.Tensor]] = None, *, th: int, tw: int) -> torch.Tensor:
+        """Parity aid: the final conv's fp32 output BEFORE the tanh (generators.py:119-121) as (1, img_ch, th*P, tw*P)."""
+        with self._on_device():
+            p = self.plan(th, tw, L.IMG_MERGED, pre_tanh=True)
+            p.set_inputs(z, maps)
+            p.run()
+        return p.out_pre[..., : self.cfg.img_ch].permute(2, 0, 1).unsqueeze(0)
 
     def drop_plans(self) -> None:
         self._plans.clear()

@@ -4,7 +4,10 @@
 order (utils.py:228, 246: one `torch.randn` for the whole z grid, then one per SSM level), so the same
 torch seed gives the same texture.  Two schedules:
 
-* ``schedule='oneshot'`` (default): the whole total_h x total_w patch grid is one device-resident forward
+* ``schedule='auto'`` (default): 'sequential' when the Generator has an attention block with gamma != 0 (a trained
+  checkpoint: only then do the two schedules differ), 'oneshot' otherwise -- so the default call always reproduces
+  the image the reference's sampler produces.
+* ``schedule='oneshot'``: the whole total_h x total_w patch grid is one device-resident forward
   (what the training-time sampler utils.py:475-527 does with `LocalPadder.set_attributes(total_h, total_w)`;
   bit-for-bit what the sequential schedule produces unless attention.gamma != 0).  No patch
   is computed twice, nothing crosses the PCIe bus between layers.
@@ -103,31 +106,55 @@ def _unwrap(netG):
 # ------------------------------------------------------------------------------------------------
 # samplers
 # ------------------------------------------------------------------------------------------------
-def generate_full_grid(netG, z_full: torch.Tensor, maps_full: Optional[Sequence[torch.Tensor]] = None, graph: bool = False) -> torch.Tensor:
+def generate_full_grid(netG, z_full: torch.Tensor, maps_full: Optional[Sequence[torch.Tensor]] = None, graph: bool = False,
+                       pre_tanh: bool = False) -> torch.Tensor:
     """One-shot forward of a whole patch grid.  z_full: (1, z_dim, th*b+2, tw*b+2) host or device fp32;
     maps_full: per level (1, 1, th*r+4, tw*r+4).  Returns the device-resident (1, img_ch, th*P, tw*P) image
-    (the engine's output buffer: valid until the next call on the same grid size)."""
+    (the engine's output buffer: valid until the next call on the same grid size).  pre_tanh=True returns the final conv's
+    fp32 output before the tanh instead (parity checks: a tenth of the outputs of a trained Generator saturate)."""
     G = _unwrap(netG)
     b = G.cfg.base_res
     th, tw = (z_full.shape[-2] - 2) // b, (z_full.shape[-1] - 2) // b
     if z_full.shape[0] != 1:
         raise ValueError("one texture per call (utils.py:341 ignores num_images as well)")
     eng = G.engine()
-    return eng.forward(z_full[0], None if maps_full is None else [m[0, 0] for m in maps_full], th=th, tw=tw,
-                       img_layout=L.IMG_MERGED, graph=graph)
+    maps = None if maps_full is None else [m[0, 0] for m in maps_full]
+    if pre_tanh:
+        return eng.forward_pre_tanh(z_full[0], maps, th=th, tw=tw)
+    return eng.forward(z_full[0], maps, th=th, tw=tw, img_layout=L.IMG_MERGED, graph=graph)
+
+
+def resolve_schedule(netG, schedule: str = "auto") -> str:
+    """'auto' -> the schedule that reproduces the reference's sampler: the one-shot pass equals the shipped sequential
+    3x3 schedule bit for bit unless the attention block contributes (attention.gamma != 0), in which case
+    the outer patches the reference drops and regenerates differ and only 'sequential' matches."""
+    if schedule not in ("auto", "oneshot", "sequential"):
+        raise ValueError("schedule must be 'auto', 'oneshot' or 'sequential'")
+    if schedule != "auto":
+        return schedule
+    att = getattr(_unwrap(netG), "attention", False)
+    gamma = getattr(att, "gamma", None) if att is not False else None
+    return "sequential" if gamma is not None and float(gamma.detach().float().cpu()) != 0.0 else "oneshot"
 
 
 def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, num_images=1, num_patches_height=3,
                                       num_patches_width=3, device="cpu", output_resolution_height=384,
-                                      output_resolution_width=384, schedule: str = "oneshot", noise=None,
+                                      output_resolution_width=384, schedule: str = "auto", noise=None,
                                       return_on_device: bool = False, graph: bool = False) -> torch.Tensor:
     """Generate one (1, img_ch, H, W) texture (utils.py:258-397).  Returns a host fp32 tensor like the
     reference (each of its sub-images is `.cpu()`-ed, utils.py:360) unless return_on_device.
 
+    schedule: 'auto' (default; see resolve_schedule), 'oneshot' or 'sequential'.
     noise: optional (z_full, maps_full) to use instead of drawing from the global host RNG.
-    graph: replay the one-shot launch list from a CUDA graph (captured on first use per grid size)."""
+    graph: replay the one-shot launch list from a CUDA graph (captured on first use per grid size).
+    base_res must be the Generator's own (the reference's sampler trusts its argument, utils.py:258; its Generator is fully
+    convolutional and ignores base_res, here the launch plan is built for the Generator's value)."""
     G = _unwrap(netG)
     n_layers_G, type_norm = G.n_layers_G, G.type_norm
+    if base_res != G.cfg.base_res:
+        raise ValueError(f"base_res={base_res} does not match the Generator's base_res={G.cfg.base_res}: pass the checkpoint's "
+                         "args.base_res (test_sample.py:68 relies on the default 4)")
+    schedule = resolve_schedule(netG, schedule)
     geo = patch_grid_geometry(output_resolution_height, output_resolution_width, n_layers_G, base_res,
                               num_patches_height, num_patches_width)
     P, th, tw = geo["P"], geo["total_h"], geo["total_w"]
@@ -142,8 +169,6 @@ def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, nu
     if schedule == "oneshot":
         img = generate_full_grid(netG, z_full, maps_full, graph=graph)[:, :, :H, :W]
         return img if return_on_device else img.cpu()
-    if schedule != "sequential":
-        raise ValueError("schedule must be 'oneshot' or 'sequential'")
 
     # ---- the shipped schedule (utils.py:317-392) with on-device halos and on-device assembly ----
     dev = next(G.parameters()).device

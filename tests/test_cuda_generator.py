@@ -45,6 +45,22 @@ def test_sequential_sampler_matches_reference(name, precision):
     print(f"{name} {precision}: sequential max-abs {err:.3e}")
 
 
+@pytest.mark.parametrize("name", ["gen_bn4_att_rep", "gen_ssm4_att_rep", "gen_bn5_gamma0_rep"])
+def test_default_sampler_call_reproduces_the_reference_sampler(name):
+    """The drop-in call (no schedule argument) returns what the reference's sampler returns: with a contributing attention block
+    (gamma != 0 in the first two fixtures) that is the sequential schedule's image, which differs from the one-shot image."""
+    import infinite_texture_gans_b200 as itg
+    d, kw, ocfg, sd, z, maps = load_case(name)
+    net = make_generator(kw, sd, "fp32", "cuda")
+    H, W = int(d["H"]), int(d["W"])
+    img = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], output_resolution_height=H, output_resolution_width=W, noise=(z, maps))
+    compare_with_golden(d, "seq", img, 1e-3)
+    want = "sequential" if float(sd["attention.gamma"]) != 0 else "oneshot"
+    assert itg.utils.resolve_schedule(net) == want
+    with pytest.raises(ValueError, match="base_res"):
+        itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], base_res=8, output_resolution_height=H, output_resolution_width=W)
+
+
 def test_forward_signature_and_patch_layout():
     """netG(z, maps, image_location) returns (nph*npw, img_ch, P, P) patches in row-major order (generators.py:86-124)."""
     import infinite_texture_gans_b200 as itg
@@ -97,7 +113,7 @@ def test_streaming_textures_equal_blocking_sampler(name):
     for _ in range(4):
         noises.append((torch.randn(z.shape, generator=g), None if maps is None else [torch.randn(m.shape, generator=g) for m in maps]))
     want = [itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], output_resolution_height=H, output_resolution_width=W,
-                                                        noise=n).clone() for n in noises]
+                                                        noise=n, schedule="oneshot").clone() for n in noises]
     got = [img.clone() for img in itg.utils.generate_textures(net, iter(noises), H, W)]
     assert len(got) == len(want)
     for a, b in zip(got, want):
@@ -216,7 +232,9 @@ def test_cli_end_to_end(tmp_path):
     torch.manual_seed(123)
     geo = O.geometry(H, W, ocfg)
     z2 = torch.randn(1, kw["z_dim"], geo["total_h"] * 4 + 2, geo["total_w"] * 4 + 2)
-    with torch.no_grad():
-        ref = O.forward_merged(sd, ocfg, z2)[:, :, :H, :W]
+    with torch.no_grad():       # the fixture's attention.gamma is 0.5: the CLI's default --schedule auto must run the shipped sequential schedule
+        ref = O.sample_patch_by_patch(sd, ocfg, H, W, z2)[:, :, :H, :W]
+        one = O.forward_merged(sd, ocfg, z2)[:, :, :H, :W]
     ref8 = (ref[0] * 0.5 + 0.5).clamp(0, 1).permute(1, 2, 0).numpy()
     assert np.abs(img - ref8).max() <= 1.5 / 255.0
+    assert (ref - one).abs().max().item() > 0.05              # ... which the one-shot pass does not reproduce for this checkpoint
