@@ -233,6 +233,14 @@ int itg_ipc_free(void* ptr);
 int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int32_t border, int32_t sides,
                    void* stream);
 
+/* Counter-based replacement of the host-side noise draw (utils.py:228, 246: torch.randn of the whole z grid / noise map, then .to(device)):
+ * fills dst (C, h, w) fp32, contiguous, with the window [y0, y0+h) x [x0, x0+w) of a standard-normal field of C x Hf x Wf values that is a
+ * pure function of (seed, field, element index): Philox4x32-10 keyed by seed, counter = (element / 4, field), Box-Muller.  Ranks / sub-images
+ * generate exactly the part they consume; windows of one field agree bit for bit wherever they overlap.  field: 0 = z, 1 + i = map of level i.
+ * Same distribution as torch.randn, not the same stream. */
+int itg_noise_normal(float* dst, int32_t C, int32_t h, int32_t w, int32_t y0, int32_t x0, int32_t Hf, int32_t Wf, uint64_t seed, uint32_t field,
+                     void* stream);
+
 /* Output stage of test_sample.py:75-79: `save_image(img * 0.5 + 0.5, path)` quantises the fp32 image with
  * torchvision's `mul(255).add_(0.5).clamp_(0, 255).to(uint8)` after the `* 0.5 + 0.5`, on the host.  This does the
  * same arithmetic (same fp32 operations in the same order, no FMA contraction: bit-identical bytes) on the device, so

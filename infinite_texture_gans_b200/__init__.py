@@ -8,7 +8,7 @@ Public surface (mirrors the reference's models/generators.py, models/layers.py a
 
 All arithmetic runs in libitg_b200.so (csrc/, C ABI in include/itg.h); there is no CPU or PyTorch fallback.
 """
-from . import config, engine, generators, halo, layers, ops, packing, utils  # noqa: F401
+from . import bands, config, engine, generators, halo, layers, ops, packing, utils  # noqa: F401
 from ._lib import ItgError, LIB_PATH  # noqa: F401
 from .config import GenConfig  # noqa: F401
 from .generators import ResidualPatchGenerator  # noqa: F401

@@ -28,7 +28,7 @@ TORCH_OF = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 
 EXPORTS = ("itg_version", "itg_last_error", "itg_conv_desc_size", "itg_conv_fwd", "itg_attention_fwd",
            "itg_pack_nchw", "itg_pack_map_taps", "itg_copy_rect", "itg_fill_frame", "itg_halo_exchange", "itg_step_advance",
-           "itg_ipc_alloc", "itg_ipc_open", "itg_ipc_close", "itg_ipc_free", "itg_image_to_u8", "itg_ssm_fwd", "itg_ssm_desc_size")
+           "itg_ipc_alloc", "itg_ipc_open", "itg_ipc_close", "itg_ipc_free", "itg_image_to_u8", "itg_ssm_fwd", "itg_ssm_desc_size", "itg_noise_normal")
 
 
 class ConvDesc(C.Structure):
@@ -107,6 +107,8 @@ def load() -> C.CDLL:
     lib.itg_fill_frame.argtypes = [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]
     lib.itg_image_to_u8.restype = C.c_int
     lib.itg_image_to_u8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.itg_noise_normal.restype = C.c_int
+    lib.itg_noise_normal.argtypes = [C.c_void_p] + [C.c_int32] * 7 + [C.c_uint64, C.c_uint32, C.c_void_p]
     lib.itg_ssm_desc_size.restype = C.c_int
     lib.itg_ssm_fwd.restype = C.c_int
     lib.itg_ssm_fwd.argtypes = [C.POINTER(SsmDesc), C.c_void_p]

@@ -109,7 +109,7 @@ template <> struct TileMode<ITG_UPCONV> { static constexpr int NPHASE = 4, NTAPS
 
 // All MMAs of one tile: NPHASE accumulators x NTAPS taps x KSTEPS 16-channel steps, fully unrolled.
 template <int MODE, int KSTEPS>
-__device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w16, uint32_t n16, uint32_t kg, uint32_t idesc, uint32_t leader) {
+__device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w16, uint32_t n16, uint32_t kg, uint32_t idesc) {
 #pragma unroll
   for (int q = 0; q < TileMode<MODE>::NPHASE; ++q) {
 #pragma unroll
@@ -121,7 +121,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w
       for (int ks = 0; ks < KSTEPS; ++ks) {
         const uint64_t adesc = desc_noswz(a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16) + shift16, PLANE_BYTES / 16, HALO_W);
         const uint64_t bdesc = desc_noswz(w16 + ((uint32_t)wt * kg + (uint32_t)(2 * ks)) * n16, n16, 8);
-        umma_f16_pred(d0 + (uint32_t)q * n16, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u, leader);
+        umma_f16(d0 + (uint32_t)q * n16, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
       }
     }
   }
@@ -275,14 +275,13 @@ conv_tile_kernel(const TileParams p) {
       ITG_ACC(1, tl);
       tc_fence_after();
       const uint32_t a16 = (a_smem + (uint32_t)(s * p.stage_bytes)) >> 4;
-      {                                                                          // one lane issues the whole tile, predicated, no branch
-        const uint32_t leader = elect_one_sync() ? 1u : 0u;
-        const uint32_t d0 = tmem_base + (uint32_t)(b * NPHASE * p.n);
-        if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc, leader);
-        else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc, leader);
-        else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc, leader);
-        umma_commit_pred(bar_empty + 8 * s, leader);                           // input stage may be refilled
-        umma_commit_pred(bar_tfull + 8 * b, leader);                           // accumulators of this tile complete
+      if (elect_one_sync()) {                                                    // one elected lane issues the whole tile from a branch that ptxas
+        const uint32_t d0 = tmem_base + (uint32_t)(b * NPHASE * p.n);            // recognises as single-threaded: descriptors stay on the uniform datapath
+        if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        umma_commit(bar_empty + 8 * s);                                        // input stage may be refilled
+        umma_commit(bar_tfull + 8 * b);                                        // accumulators of this tile complete
       }
       __syncwarp();
       ITG_ACC(2, tl);

@@ -340,22 +340,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t adesc = make_smem_desc(sa, p.sbo_enc, p.layout_type);
           const uint64_t bdesc = make_smem_desc(sa + p.a_stride, p.sbo_enc, p.layout_type);
           const int nk = (c == p.nchunks - 1) ? p.ksteps_last : (p.kc >> 4);
-          {                                       // branch-free: the elected lane's predicate guards each instruction,
-            const uint32_t leader = elect_one_sync() ? 1u : 0u;   // descriptors stay on the uniform datapath
-            umma_f16_pred(dcol, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u, leader);           // +32 B (16 channels) per K step
-            umma_f16_pred(dcol, adesc + 2, bdesc + 2, p.idesc, 1u, (nk > 1) ? leader : 0u);
-            umma_f16_pred(dcol, adesc + 4, bdesc + 4, p.idesc, 1u, (nk > 2) ? leader : 0u);
-            umma_f16_pred(dcol, adesc + 6, bdesc + 6, p.idesc, 1u, (nk > 3) ? leader : 0u);
-            if (p.cluster == 1) umma_commit_pred(bar_empty + 8 * s, leader);   // frees the stage when these MMAs have read it
-            else umma_commit_mc_pred(bar_empty + 8 * s, cmask, leader);        // ... in every CTA of the cluster
+          if (elect_one_sync()) {                 // single-threaded branch: ptxas keeps the descriptors on the uniform datapath (no ELECT / R2UR loop)
+            umma_f16(dcol, adesc, bdesc, p.idesc, it > 0 ? 1u : 0u);                        // +32 B (16 channels) per K step
+            if (nk > 1) umma_f16(dcol, adesc + 2, bdesc + 2, p.idesc, 1u);
+            if (nk > 2) umma_f16(dcol, adesc + 4, bdesc + 4, p.idesc, 1u);
+            if (nk > 3) umma_f16(dcol, adesc + 6, bdesc + 6, p.idesc, 1u);
+            if (p.cluster == 1) umma_commit(bar_empty + 8 * s);                             // frees the stage when these MMAs have read it
+            else umma_commit_mc_pred(bar_empty + 8 * s, cmask, 1u);                         // ... in every CTA of the cluster
+            if (t == ntaps - 1 && c == p.nchunks - 1) umma_commit(bar_tfull + 8 * b);       // accumulators of this item complete
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
           ITG_UACC(2, tl);
         }
       }
-      umma_commit_pred(bar_tfull + 8 * b, elect_one_sync() ? 1u : 0u);   // accumulators of this item complete
-      __syncwarp();
     }
     if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[2] = dacc[0]; p.dbg[3] = dacc[1]; p.dbg[4] = dacc[2]; }
   } else if (warp >= 4) {                                              // ---- epilogue: both groups drain every item, group g takes the

@@ -185,4 +185,44 @@ __global__ void fill_frame_kernel(T* __restrict__ t, int h, int w, int c, int bo
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// counter-based noise: a window of a standard-normal FIELD, generated where it is consumed
+// ------------------------------------------------------------------------------------------------
+// utils.build_z / build_maps (utils.py:221-256) draw the full-grid noise with torch.randn on the host and ship it to the device; for
+// a 65536^2 texture that is 2.2 GB of latents and seconds of host time per pass.  Here element e = (c * Hf + y) * Wf + x of field
+// `stream` (0 = z, 1 + i = noise map of level i) is a pure function of (seed, stream, e): Philox4x32-10 (Salmon et al., SC'11; the
+// Random123 reference known-answer vectors are checked in tests/) keyed by the seed, counter = (e / 4, stream), Box-Muller on the two
+// pairs of outputs.  Any rank can therefore generate exactly its own band (or sub-image) of the same field, with no host work, no
+// PCIe traffic and no exchange; it matches torch.randn in distribution only.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void noise_normal_kernel(float* __restrict__ dst, int C, int h, int w, int y0, int x0, int Hf, int Wf, uint32_t seed_lo,
+                                    uint32_t seed_hi, uint32_t stream) {
+  const size_t total = (size_t)C * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w), y = (int)((i / w) % h), c = (int)(i / ((size_t)w * h));
+    const unsigned long long e = ((unsigned long long)c * Hf + (unsigned long long)(y0 + y)) * Wf + (unsigned long long)(x0 + x);
+    const unsigned long long g = e >> 2;
+    uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), stream, 0u};
+    philox4x32_10(ctr, seed_lo, seed_hi);
+    const int pair = (int)(e & 2);                                    // outputs (0,1) serve elements 0,1 of the group, (2,3) elements 2,3
+    const float u1 = ((float)ctr[pair] + 1.0f) * 2.3283064365386963e-10f;        // (0, 1]
+    const float u2 = (float)ctr[pair + 1] * 2.3283064365386963e-10f;             // [0, 1]
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    dst[i] = rad * ((e & 1) ? sn : cs);
+  }
+}
+
 }  // namespace itg

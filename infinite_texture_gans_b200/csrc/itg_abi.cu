@@ -513,6 +513,8 @@ int launch_ssm(const itg_ssm_desc& d, cudaStream_t st) {
     if (!dbg_buf) ITG_CUDA(cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long)));
     ITG_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st));
     p.dbg = dbg_buf;
+    const char* e = getenv("ITG_SSM_EXP");                          // timing experiments (wrong results), only read in debug mode
+    p.exp = e ? atoi(e) : 0;
   }
   static bool attr_set[MAX_DEVICES][2] = {{false, false}};
   const int dev = current_device();
@@ -758,6 +760,16 @@ int itg_fill_frame(int32_t dtype, void* t, int32_t h, int32_t w, int32_t c, int3
   else if (dtype == ITG_F16) itg::fill_frame_kernel<__half><<<blocks, 256, 0, st>>>((__half*)t, h, w, c, border, sides);
   else if (dtype == ITG_BF16) itg::fill_frame_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)t, h, w, c, border, sides);
   else return fail(ITG_ERR_INVALID, "fill_frame: bad dtype");
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+int itg_noise_normal(float* dst, int32_t C, int32_t h, int32_t w, int32_t y0, int32_t x0, int32_t Hf, int32_t Wf, uint64_t seed, uint32_t field,
+                     void* stream) {
+  if (!dst || C < 1 || h < 1 || w < 1 || y0 < 0 || x0 < 0 || y0 + h > Hf || x0 + w > Wf)
+    return fail(ITG_ERR_INVALID, "noise_normal: window %dx%d at (%d,%d) outside the %dx%d field", h, w, y0, x0, Hf, Wf);
+  const int blocks = blocks_for((size_t)C * h * w, 256);
+  itg::noise_normal_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, C, h, w, y0, x0, Hf, Wf, (uint32_t)seed, (uint32_t)(seed >> 32), field);
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;
 }

@@ -50,12 +50,12 @@ constexpr int SSM_OFF_W1 = SSM_HDR;
 constexpr int SSM_OFF_TAPS = SSM_OFF_W1 + SSM_W1_BYTES;                // 2 buffers
 constexpr int SSM_OFF_WIN = SSM_OFF_TAPS + 2 * SSM_TAPS_BYTES;         // 16-bit staging of the map window
 constexpr int SSM_OFF_A = SSM_OFF_WIN + 512;                           // 16 planes of 180 halo pixels x 16 B
-constexpr int SSM_OFF_W2 = SSM_OFF_A + SSM_KG * PLANE_BYTES;           // [tap 9][k-group 16][n_blk][16 B]
+constexpr int SSM_OFF_W2 = SSM_OFF_A + SSM_KG * PLANE_BYTES;           // [tap 9][k-group 16][64 rows, n_blk used][16 B]
 constexpr int SSM_TMEM_MLP = 256;                                      // TMEM columns 256..511: the two m1 row blocks; 0..2*n_blk: embed accumulators
 static_assert(SSM_WIN_N * 2 <= 512, "map window staging");
 static_assert(SSM_OFF_A % 128 == 0 && SSM_OFF_W2 % 128 == 0, "operand alignment");
 
-__host__ __device__ constexpr int ssm_smem_bytes(int n_blk) { return SSM_OFF_W2 + 9 * SSM_KG * n_blk * 16 + 1024; }
+__host__ __device__ constexpr int ssm_smem_bytes(int) { return SSM_OFF_W2 + 9 * SSM_KG * SSM_NBLK_MAX * 16 + 1024; }      // weight image: fixed row pitch
 
 struct SsmParams {
   int h, w;                 // interior size of the modulated tensor / output
@@ -67,6 +67,8 @@ struct SsmParams {
   int n_pad, n_blk, nblocks;
   uint32_t idesc_mlp, idesc_emb;
   unsigned long long* dbg;  // optional cycle counters of CTA 0 (ITG_TILE_DBG=1)
+  int exp;                  // developer experiments (ITG_SSM_EXP bit mask: WRONG RESULTS, timing only): 1 no proxy fence, 2 no plane stores,
+                            // 4 no epilogue math / stores, 8 one tap per k-step
   EpiParams ep;
 };
 
@@ -75,6 +77,26 @@ struct SsmParams {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+
+// 32 consecutive TMEM columns of this thread's lane, without waiting: the registers may only be read after tmem_ld_wait(r)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// ... the wait names the registers as in/out operands so that no use of them can be scheduled before it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                 "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+constexpr int SSM_GROUPS = SSM_KSTEPS / 2;                   // the converters hand the A planes over in groups of two k-steps (32 channels)
 
 template <typename T>
 __global__ void __launch_bounds__(SSM_THREADS, 1)
@@ -108,7 +130,7 @@ ssm_fused_kernel(const SsmParams p) {
     }
     mbar_init(bar_mlp_full, 1);
     mbar_init(bar_mlp_empty, 6);
-    for (int i = 0; i < SSM_KSTEPS; ++i) {
+    for (int i = 0; i < SSM_GROUPS; ++i) {
       mbar_init(bar_a_full + 8 * i, 6);
       mbar_init(bar_a_empty + 8 * i, 1);
     }
@@ -126,7 +148,7 @@ ssm_fused_kernel(const SsmParams p) {
       const int ng = nb * p.n_blk + n;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (ng < p.n_pad) v = *reinterpret_cast<const uint4*>(w2 + ((size_t)t * p.n_pad + ng) * SSM_K + j * 8);
-      sts128(w2s + (uint32_t)i * 16u, v.x, v.y, v.z, v.w);
+      sts128(w2s + (uint32_t)(((t * SSM_KG + j) * SSM_NBLK_MAX + n) * 16), v.x, v.y, v.z, v.w);     // row pitch fixed at 64: compile-time descriptors
     }
     const T* w1 = reinterpret_cast<const T*>(p.w1);
     for (int i = threadIdx.x; i < 2 * SSM_K; i += SSM_THREADS) {
@@ -197,9 +219,13 @@ ssm_fused_kernel(const SsmParams p) {
       mbar_arrive(bar_taps_full + 8 * tb);
     }
   } else if (warp == SSM_WARP_MMA) {
-    // ---- MMA warp: uniform control flow, one elected lane issues (predicated) ----
+    // ---- MMA warp.  Waits run warp-uniform (lane 0 polls, __syncwarp releases the warp); the MMAs of one k-step are issued inside an
+    //      `if (elect_one_sync())` block with every descriptor a compile-time offset from warp-uniform values: ptxas then keeps the
+    //      whole issue sequence on the uniform datapath (UTCHMMA back to back, 2-4 uniform ALU instructions in between).  A per-lane
+    //      predicate on the instruction instead makes it build each descriptor in vector registers and move it over with an
+    //      ELECT / R2UR / BRA.U.ANY loop: measured 88 cycles per MMA, more than the MMA itself (profiles/r02_notes.md). ----
     const uint32_t w1_16 = (sbase + SSM_OFF_W1) >> 4, w2_16 = (sbase + SSM_OFF_W2) >> 4, a16 = (sbase + SSM_OFF_A) >> 4;
-    const uint32_t n16 = (uint32_t)p.n_blk;
+    constexpr uint32_t n16 = SSM_NBLK_MAX;                             // row pitch of the parked weight image (the MMA's N is in idesc)
     unsigned long long dacc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
     auto issue_mlp = [&](int it) {
@@ -210,13 +236,14 @@ ssm_fused_kernel(const SsmParams p) {
       }
       __syncwarp();
       tc_fence_after();
-      const uint32_t leader = elect_one_sync() ? 1u : 0u;
-      const uint32_t t16 = (sbase + SSM_OFF_TAPS + (uint32_t)tb * SSM_TAPS_BYTES) >> 4;
-      const uint64_t bdesc = desc_noswz(w1_16, SSM_K, 8);
-      umma_f16_pred(tmem_base + SSM_TMEM_MLP, desc_noswz(t16, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u, leader);
-      umma_f16_pred(tmem_base + SSM_TMEM_MLP + SSM_K, desc_noswz(t16 + 128, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u, leader);
-      umma_commit_pred(bar_taps_empty + 8 * tb, leader);
-      umma_commit_pred(bar_mlp_full, leader);
+      if (elect_one_sync()) {
+        const uint32_t t16 = (sbase + SSM_OFF_TAPS + (uint32_t)tb * SSM_TAPS_BYTES) >> 4;
+        const uint64_t bdesc = desc_noswz(w1_16, SSM_K, 8);
+        umma_f16(tmem_base + SSM_TMEM_MLP, desc_noswz(t16, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u);
+        umma_f16(tmem_base + SSM_TMEM_MLP + SSM_K, desc_noswz(t16 + 128, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u);
+        umma_commit(bar_taps_empty + 8 * tb);
+        umma_commit(bar_mlp_full);
+      }
       __syncwarp();
     };
     if (n_my > 0) issue_mlp(0);
@@ -226,30 +253,34 @@ ssm_fused_kernel(const SsmParams p) {
       if (lane == 0) mbar_wait(bar_acc_empty + 8 * b, (((uint32_t)it >> 1) & 1u) ^ 1u);
       __syncwarp();
       ITG_SACC(1, tl);
-      const uint32_t d = tmem_base + (uint32_t)b * n16;
-      for (int ks = 0; ks < SSM_KSTEPS; ++ks) {
-        if (lane == 0) mbar_wait(bar_a_full + 8 * ks, (uint32_t)it & 1u);
+      const uint32_t d = tmem_base + (uint32_t)(b * p.n_blk);
+#pragma unroll
+      for (int g = 0; g < SSM_GROUPS; ++g) {
+        if (lane == 0) mbar_wait(bar_a_full + 8 * g, (uint32_t)it & 1u);
         __syncwarp();
         ITG_SACC(2, tl);
         tc_fence_after();
-        {
-          const uint32_t leader = elect_one_sync() ? 1u : 0u;
-          const uint32_t ak = a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16);
-          const uint32_t wk = w2_16 + (uint32_t)(2 * ks) * n16;
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const uint32_t shift16 = (uint32_t)((t / 3) * HALO_W + (t % 3));
-            umma_f16_pred(d, desc_noswz(ak + shift16, PLANE_BYTES / 16, HALO_W), desc_noswz(wk + (uint32_t)(t * SSM_KG) * n16, n16, 8),
-                          p.idesc_emb, (ks > 0 || t > 0) ? 1u : 0u, leader);
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int ks = 2 * g + k2;
+            const uint32_t ak = a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16);
+            const uint32_t wk = w2_16 + (uint32_t)(2 * ks) * n16;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if ((p.exp & 8) && t > 0) break;
+              const uint32_t shift16 = (uint32_t)((t / 3) * HALO_W + (t % 3));
+              umma_f16(d, desc_noswz(ak + shift16, PLANE_BYTES / 16, HALO_W), desc_noswz(wk + (uint32_t)(t * SSM_KG) * n16, n16, 8),
+                       p.idesc_emb, (ks > 0 || t > 0) ? 1u : 0u);
+            }
           }
-          umma_commit_pred(bar_a_empty + 8 * ks, leader);               // the plane pair may be overwritten with the next tile's values
+          umma_commit(bar_a_empty + 8 * g);                           // these four planes may be overwritten with the next tile's values
+          if (g == SSM_GROUPS - 1) umma_commit(bar_acc_full + 8 * b);
         }
         __syncwarp();
         ITG_SACC(3, tl);
-        if (ks == 2 && it + 1 < n_my) { issue_mlp(it + 1); ITG_SACC(0, tl); }     // 27 embed MMAs are queued while this waits for the converters
+        if (g == 0 && it + 1 < n_my) { issue_mlp(it + 1); ITG_SACC(0, tl); }     // 18 embed MMAs are queued while this waits for the converters
       }
-      umma_commit_pred(bar_acc_full + 8 * b, elect_one_sync() ? 1u : 0u);
-      __syncwarp();
     }
     if (p.dbg && blockIdx.x == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[i] = dacc[i];
   } else if (warp >= SSM_WARP_CVT) {
@@ -266,27 +297,36 @@ ssm_fused_kernel(const SsmParams p) {
       __syncwarp();
       ITG_SACC(0, tl);
       tc_fence_after();
-      for (int ks = 0; ks < SSM_KSTEPS; ++ks) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)(16 * ks), v);
-        uint32_t w[8];
+      // groups of 32 channels (two k-steps, four planes): one TMEM load, one proxy fence and one arrival per group; the next group's
+      // load is in flight while this one is packed and stored (a converter warp working chunk by chunk was the critical path)
+      uint32_t r[32];
+      tmem_ld32_issue(trow, r);
+      tmem_ld_wait(r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = pack2<T>(fmaxf(v[2 * i], 0.f), fmaxf(v[2 * i + 1], 0.f));
-        if (lane == 0) mbar_wait(bar_a_empty + 8 * ks, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's MMAs have read this plane pair
+      for (int g = 0; g < SSM_GROUPS; ++g) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
+        if (g + 1 < SSM_GROUPS) tmem_ld32_issue(trow + (uint32_t)(32 * (g + 1)), r);
+        if (lane == 0) mbar_wait(bar_a_empty + 8 * g, ((uint32_t)it & 1u) ^ 1u);       // the previous tile's MMAs have read these planes
         __syncwarp();
         ITG_SACC(1, tl);
-        if (hp_ok) {
-          sts128(dst + (uint32_t)((2 * ks) * PLANE_BYTES), w[0], w[1], w[2], w[3]);
-          sts128(dst + (uint32_t)((2 * ks + 1) * PLANE_BYTES), w[4], w[5], w[6], w[7]);
+        if (hp_ok && !(p.exp & 2)) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            sts128(dst + (uint32_t)((4 * g + q4) * PLANE_BYTES), w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
         }
-        fence_proxy_async();
+        if (!(p.exp & 1)) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a_full + 8 * ks);
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * g);
+        if (g + 1 < SSM_GROUPS) tmem_ld_wait(r);
+        if (g + 2 == SSM_GROUPS) {                                     // the last group is in registers: the m1 accumulator may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_mlp_empty);
+        }
         ITG_SACC(2, tl);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_mlp_empty);
     }
     if (p.dbg && blockIdx.x == 0 && warp == SSM_WARP_CVT && lane == 0) for (int i = 0; i < 3; ++i) p.dbg[4 + i] = dacc[i];
   } else {
@@ -329,7 +369,7 @@ ssm_fused_kernel(const SsmParams p) {
         if (!live[j]) continue;
         float v[16];
         tmem_ld16(trow + (uint32_t)(16 * c), v);
-        if (!ok[j]) continue;
+        if (!ok[j] || (p.exp & 4)) continue;
         float xf[8], yv[8];
         {
           const Vec8<T> t8 = *reinterpret_cast<const Vec8<T>*>(&xr[j]);

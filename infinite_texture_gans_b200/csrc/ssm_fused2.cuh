@@ -29,7 +29,7 @@ constexpr int SSM2_OFF_A = SSM2_OFF_WIN + 512;
 constexpr int SSM2_OFF_W2 = SSM2_OFF_A + SSM_KG * PLANE_BYTES;          // [tap 9][k-group 16][n_half][16 B]
 static_assert(SSM2_OFF_A % 128 == 0 && SSM2_OFF_W2 % 128 == 0, "operand alignment");
 
-__host__ __device__ constexpr int ssm2_smem_bytes(int n_half) { return SSM2_OFF_W2 + 9 * SSM_KG * n_half * 16 + 1024; }
+__host__ __device__ constexpr int ssm2_smem_bytes(int) { return SSM2_OFF_W2 + 9 * SSM_KG * SSM_NBLK_MAX * 16 + 1024; }     // weight image: fixed row pitch
 
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -47,7 +47,18 @@ __device__ __forceinline__ void umma2_f16_pred(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(leader)
       : "memory");
 }
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // all MMAs issued so far by this thread arrive, when complete, on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void umma2_commit_pred(uint32_t bar, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
@@ -56,13 +67,15 @@ __device__ __forceinline__ void umma2_commit_pred(uint32_t bar, uint32_t leader)
       ::"r"(bar), "r"(leader), "h"((uint16_t)3)
       : "memory");
 }
-// arrive on the barrier at the same offset in CTA `cta` of the cluster (release at cluster scope: the arriving warp's shared-memory
-// writes and TMEM reads are ordered before the leader's MMA issue)
+// arrive on the barrier at the same offset in CTA `cta` of the cluster.  The arriving warp has already made its shared-memory writes
+// visible to the async proxy (fence.proxy.async) / finished its TMEM reads (tcgen05.fence::before_thread_sync), and the data it guards
+// never leaves its own SM: the default (CTA-scope) release is what CUTLASS's ClusterBarrier::arrive(cta_id) uses for the same hand-off.
+// A cluster-scope release here cost ~800 cycles per arrival (measured: 965 vs 147 cycles per converted plane pair).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta)
       : "memory");
 }
@@ -70,7 +83,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -126,7 +139,7 @@ ssm_fused2_kernel(const SsmParams p) {
     }
     mbar_init(bar_mlp_full, 1);
     mbar_init(bar_mlp_empty, 12);
-    for (int i = 0; i < SSM_KSTEPS; ++i) {
+    for (int i = 0; i < SSM_GROUPS; ++i) {
       mbar_init(bar_a_full + 8 * i, 12);
       mbar_init(bar_a_empty + 8 * i, 1);
     }
@@ -144,7 +157,7 @@ ssm_fused2_kernel(const SsmParams p) {
       const int ng = n0 + (int)rank * n_half + n;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (ng < p.n_pad) v = *reinterpret_cast<const uint4*>(w2 + ((size_t)t * p.n_pad + ng) * SSM_K + j * 8);
-      sts128(w2s + (uint32_t)i * 16u, v.x, v.y, v.z, v.w);
+      sts128(w2s + (uint32_t)(((t * SSM_KG + j) * SSM_NBLK_MAX + n) * 16), v.x, v.y, v.z, v.w);     // row pitch fixed at 64: compile-time descriptors
     }
     const T* w1 = reinterpret_cast<const T*>(p.w1);
     for (int i = threadIdx.x; i < 2 * 64; i += SSM_THREADS) {
@@ -219,59 +232,64 @@ ssm_fused2_kernel(const SsmParams p) {
     }
   } else if (warp == SSM_WARP_MMA) {
     if (rank == 0) {
-      // ---- MMA warp of the LEADER: issues for both CTAs ----
+      // ---- MMA warp of the LEADER: issues for both CTAs (elect-guarded blocks, descriptors on the uniform datapath: see ssm_fused.cuh) ----
       const uint32_t w1_16 = (sbase + SSM2_OFF_W1) >> 4, w2_16 = (sbase + SSM2_OFF_W2) >> 4, a16 = (sbase + SSM2_OFF_A) >> 4;
-      const uint32_t nh16 = (uint32_t)n_half;
+      constexpr uint32_t nh16 = SSM_NBLK_MAX;                          // row pitch of the parked weight image (the MMA's N is in idesc)
       unsigned long long dacc[4] = {0, 0, 0, 0};
       long long tl = p.dbg ? clock64() : 0;
       auto issue_mlp = [&](int it) {
         const int tb = it & 1;
         if (lane == 0) {
-          mbar_wait_cluster(bar_taps_full + 8 * tb, ((uint32_t)it >> 1) & 1u);
-          mbar_wait_cluster(bar_mlp_empty, ((uint32_t)it & 1u) ^ 1u);
+          mbar_wait(bar_taps_full + 8 * tb, ((uint32_t)it >> 1) & 1u);
+          mbar_wait(bar_mlp_empty, ((uint32_t)it & 1u) ^ 1u);
         }
         __syncwarp();
         tc_fence_after();
-        const uint32_t leader = elect_one_sync() ? 1u : 0u;
-        const uint32_t t16 = (sbase + SSM2_OFF_TAPS + (uint32_t)tb * SSM_TAPS_BYTES) >> 4;
-        const uint64_t bdesc = desc_noswz(w1_16, 64, 8);
-        umma2_f16_pred(tmem_base + SSM_TMEM_MLP, desc_noswz(t16, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u, leader);
-        umma2_f16_pred(tmem_base + SSM_TMEM_MLP + SSM_K, desc_noswz(t16 + 128, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u, leader);
-        umma2_commit_pred(bar_taps_empty + 8 * tb, leader);
-        umma2_commit_pred(bar_mlp_full, leader);
+        if (elect_one_sync()) {
+          const uint32_t t16 = (sbase + SSM2_OFF_TAPS + (uint32_t)tb * SSM_TAPS_BYTES) >> 4;
+          const uint64_t bdesc = desc_noswz(w1_16, 64, 8);
+          umma2_f16(tmem_base + SSM_TMEM_MLP, desc_noswz(t16, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u);
+          umma2_f16(tmem_base + SSM_TMEM_MLP + SSM_K, desc_noswz(t16 + 128, SSM_TAPS_ROWS, 8), bdesc, p.idesc_mlp, 0u);
+          umma2_commit(bar_taps_empty + 8 * tb);
+          umma2_commit(bar_mlp_full);
+        }
         __syncwarp();
       };
       if (n_my > 0) issue_mlp(0);
       ITG_SACC(0, tl);
       for (int it = 0; it < n_my; ++it) {
         const int b = it & 1;
-        if (lane == 0) mbar_wait_cluster(bar_acc_empty + 8 * b, (((uint32_t)it >> 1) & 1u) ^ 1u);
+        if (lane == 0) mbar_wait(bar_acc_empty + 8 * b, (((uint32_t)it >> 1) & 1u) ^ 1u);
         __syncwarp();
         ITG_SACC(1, tl);
         const uint32_t d = tmem_base + (uint32_t)(b * p.n_blk);
-        for (int ks = 0; ks < SSM_KSTEPS; ++ks) {
-          if (lane == 0) mbar_wait_cluster(bar_a_full + 8 * ks, (uint32_t)it & 1u);
+#pragma unroll
+        for (int g = 0; g < SSM_GROUPS; ++g) {
+          if (lane == 0) mbar_wait(bar_a_full + 8 * g, (uint32_t)it & 1u);
           __syncwarp();
           ITG_SACC(2, tl);
           tc_fence_after();
-          {
-            const uint32_t leader = elect_one_sync() ? 1u : 0u;
-            const uint32_t ak = a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16);
-            const uint32_t wk = w2_16 + (uint32_t)(2 * ks) * nh16;
+          if (elect_one_sync()) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const uint32_t shift16 = (uint32_t)((t / 3) * HALO_W + (t % 3));
-              umma2_f16_pred(d, desc_noswz(ak + shift16, PLANE_BYTES / 16, HALO_W), desc_noswz(wk + (uint32_t)(t * SSM_KG) * nh16, nh16, 8),
-                             p.idesc_emb, (ks > 0 || t > 0) ? 1u : 0u, leader);
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const int ks = 2 * g + k2;
+              const uint32_t ak = a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16);
+              const uint32_t wk = w2_16 + (uint32_t)(2 * ks) * nh16;
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                if ((p.exp & 8) && t > 0) break;
+                const uint32_t shift16 = (uint32_t)((t / 3) * HALO_W + (t % 3));
+                umma2_f16(d, desc_noswz(ak + shift16, PLANE_BYTES / 16, HALO_W), desc_noswz(wk + (uint32_t)(t * SSM_KG) * nh16, nh16, 8),
+                          p.idesc_emb, (ks > 0 || t > 0) ? 1u : 0u);
+              }
             }
-            umma2_commit_pred(bar_a_empty + 8 * ks, leader);
+            umma2_commit(bar_a_empty + 8 * g);
+            if (g == SSM_GROUPS - 1) umma2_commit(bar_acc_full + 8 * b);
           }
           __syncwarp();
           ITG_SACC(3, tl);
-          if (ks == 2 && it + 1 < n_my) { issue_mlp(it + 1); ITG_SACC(0, tl); }
+          if (g == 0 && it + 1 < n_my) { issue_mlp(it + 1); ITG_SACC(0, tl); }
         }
-        umma2_commit_pred(bar_acc_full + 8 * b, elect_one_sync() ? 1u : 0u);
-        __syncwarp();
       }
       if (p.dbg && blockIdx.x == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[i] = dacc[i];
     }
@@ -289,27 +307,36 @@ ssm_fused2_kernel(const SsmParams p) {
       __syncwarp();
       ITG_SACC(0, tl);
       tc_fence_after();
-      for (int ks = 0; ks < SSM_KSTEPS; ++ks) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)(16 * ks), v);
-        uint32_t w[8];
+      // groups of 32 channels (two k-steps, four planes): one TMEM load, one proxy fence and one (remote) arrival per group; the next
+      // group's load is in flight while this one is packed and stored
+      uint32_t r[32];
+      tmem_ld32_issue(trow, r);
+      tmem_ld_wait(r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = pack2<T>(fmaxf(v[2 * i], 0.f), fmaxf(v[2 * i + 1], 0.f));
-        if (lane == 0) mbar_wait_cluster(bar_a_empty + 8 * ks, ((uint32_t)it & 1u) ^ 1u);
+      for (int g = 0; g < SSM_GROUPS; ++g) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
+        if (g + 1 < SSM_GROUPS) tmem_ld32_issue(trow + (uint32_t)(32 * (g + 1)), r);
+        if (lane == 0) mbar_wait_cluster(bar_a_empty + 8 * g, ((uint32_t)it & 1u) ^ 1u);
         __syncwarp();
         ITG_SACC(1, tl);
-        if (hp_ok) {
-          sts128(dst + (uint32_t)((2 * ks) * PLANE_BYTES), w[0], w[1], w[2], w[3]);
-          sts128(dst + (uint32_t)((2 * ks + 1) * PLANE_BYTES), w[4], w[5], w[6], w[7]);
+        if (hp_ok && !(p.exp & 2)) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            sts128(dst + (uint32_t)((4 * g + q4) * PLANE_BYTES), w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
         }
-        fence_proxy_async();
+        if (!(p.exp & 1)) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bar_a_full + 8 * ks, 0u);
+        if (lane == 0) mbar_arrive_cluster(bar_a_full + 8 * g, 0u);
+        if (g + 1 < SSM_GROUPS) tmem_ld_wait(r);
+        if (g + 2 == SSM_GROUPS) {                                     // the last group is in registers: the m1 accumulator may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(bar_mlp_empty, 0u);
+        }
         ITG_SACC(2, tl);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar_mlp_empty, 0u);
     }
     if (p.dbg && blockIdx.x == 0 && warp == SSM_WARP_CVT && lane == 0) for (int i = 0; i < 3; ++i) p.dbg[4 + i] = dacc[i];
   } else {
@@ -350,7 +377,7 @@ ssm_fused2_kernel(const SsmParams p) {
         if (!live[j]) continue;
         float v[16];
         tmem_ld16(trow + (uint32_t)(16 * c), v);
-        if (!ok[j]) continue;
+        if (!ok[j] || (p.exp & 4)) continue;
         float xf[8], yv[8];
         {
           const Vec8<T> t8 = *reinterpret_cast<const Vec8<T>*>(&xr[j]);

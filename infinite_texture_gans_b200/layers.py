@@ -34,15 +34,23 @@ class LocalPadder:
 
 
 def init_weight(m: nn.Module) -> None:
-    """Initialisation scheme of utils.py:745-762: orthogonal conv / linear weights, zero biases,
-    BatchNorm weight ~ N(1, 0.02)."""
-    if isinstance(m, (nn.Conv2d, nn.Linear)):
+    """Initialisation scheme of utils.py:745-762, selected by class NAME like the reference (`classname.find(...)`): orthogonal
+    (gain 1) weights and zero biases for anything called *Conv* or *Linear*, weight ~ N(1, 0.02) and zero bias for *Batch*
+    (affine norms only), orthogonal weights for *Embedding*.  Consumes the global RNG exactly like the reference, so the same
+    seed gives the same "random-init weights" (pinned by tests/golden/aux.npz)."""
+    name = m.__class__.__name__
+    if name.find("Conv") != -1 or name.find("Linear") != -1:
+        if getattr(m, "weight", None) is None:     # containers such as conv2d_lp: their nn.Conv2d child is visited by .apply()
+            return
         nn.init.orthogonal_(m.weight, gain=1)
         if m.bias is not None:
             nn.init.zeros_(m.bias)
-    elif isinstance(m, nn.BatchNorm2d) and m.weight is not None:
-        nn.init.normal_(m.weight, 1.0, 0.02)
-        nn.init.zeros_(m.bias)
+    elif name.find("Batch") != -1:
+        if m.weight is not None:
+            nn.init.normal_(m.weight, 1.0, 0.02)
+            nn.init.zeros_(m.bias)
+    elif name.find("Embedding") != -1:
+        nn.init.orthogonal_(m.weight, gain=1)
 
 
 class _NoForward(nn.Module):

@@ -80,6 +80,36 @@ def draw_noise(num_images: int, z_dim: int, base_res: int, n_layers_G: int, map_
     return z, maps
 
 
+def noise_window(shape_full: Tuple[int, int, int], window: Tuple[int, int, int, int], seed: int, field: int, device) -> torch.Tensor:
+    """Window (y0, y1, x0, x1) of the counter-based standard-normal field `field` of shape (C, Hf, Wf) (include/itg.h itg_noise_normal),
+    generated on `device`.  A pure function of (seed, field, position): any two windows agree where they overlap."""
+    C, Hf, Wf = shape_full
+    y0, y1, x0, x1 = window
+    out = torch.empty((C, y1 - y0, x1 - x0), dtype=torch.float32, device=device)
+    lib = L.load()
+    with torch.cuda.device(out.device):
+        L.check(lib.itg_noise_normal(L.ptr(out), C, y1 - y0, x1 - x0, y0, x0, Hf, Wf, int(seed) & 0xFFFFFFFFFFFFFFFF, field, L.stream_ptr()))
+    return out
+
+
+def draw_noise_device(cfg, total_h: int, total_w: int, seed: int, rows: Optional[Tuple[int, int]] = None, device="cuda"):
+    """Device-side counterpart of `draw_noise` / utils.build_z + build_maps (utils.py:221-256) for large grids: the noise of patch rows
+    `rows` = (r0, r1) (default: all) of a total_h x total_w grid, generated on the device from the counter-based generator -- no host
+    draw, no host -> device copy, and every rank / sub-image sees the same field.  Same distribution as the reference's torch.randn
+    draws, different stream.  Returns (z (z_dim, rows*b+2, W), [map_i (rows*r_i+4, W_i)] or None), the layout
+    `Plan.set_inputs` / `RowBandSampler.set_band_noise` take."""
+    b = cfg.base_res
+    r0, r1 = rows if rows is not None else (0, total_h)
+    z = noise_window((cfg.z_dim, total_h * b + 2, total_w * b + 2), (r0 * b, r1 * b + 2, 0, total_w * b + 2), seed, 0, device)
+    maps = None
+    if cfg.type_norm == "SSM":
+        maps = []
+        for i in range(cfg.n_layers_G):
+            r = b * 2 ** i
+            maps.append(noise_window((1, total_h * r + 4, total_w * r + 4), (r0 * r, r1 * r + 4, 0, total_w * r + 4), seed, 1 + i, device)[0])
+    return z, maps
+
+
 def build_z(num_images=1, z_dim=128, base_res=4, num_patches_height=3, num_patches_width=3, total_num_patches_height=3,
             total_num_patches_width=3, device="cpu"):
     """utils.py:221-234: overlapping sub-image crops of the full latent grid (with its random 1-px ring)."""

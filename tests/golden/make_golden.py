@@ -15,6 +15,8 @@ Fixtures:
                   'seq'  = utils.sample_from_gen_PatchByPatch_test (utils.py:258-397), 3x3 sub-image stepping
                   'one'  = one forward with LocalPadder.set_attributes(total_h,total_w) (the train-time call,
                            utils.py:475-527), merged with utils.merge_patches_into_image
+  aux.npz      -- utils.build_z / utils.build_maps outputs (utils.py:221-256) and utils.init_weight results (utils.py:745-762)
+                  under fixed seeds: pins the host-side noise plumbing and the "random-init weights" scheme.
   localpad.npz -- integer-coded tensors pushed through models.layers.LocalPadder in eval mode for a whole
                   sequential sweep (all location classes) and both outer paddings: pins the halo indexing.
 """
@@ -147,6 +149,31 @@ def localpad_case():
     print("localpad: done")
 
 
+def aux_case():
+    """build_z / build_maps (noise draw + overlapping sub-image crops) and init_weight, straight from the reference."""
+    import torch.nn as nn
+    out = {}
+    torch.manual_seed(71)
+    z = ref_utils.build_z(num_images=1, z_dim=6, base_res=4, num_patches_height=3, num_patches_width=3,
+                          total_num_patches_height=5, total_num_patches_width=7)
+    out["build_z"] = z.numpy()
+    torch.manual_seed(72)
+    maps = ref_utils.build_maps(num_images=1, map_dim=1, n_layers_G=3, base_res=4, num_patches_height=3, num_patches_width=3,
+                                total_num_patches_height=5, total_num_patches_width=7)
+    for i, m in enumerate(maps):
+        out[f"build_maps{i}"] = m.numpy()
+    torch.manual_seed(73)
+    mods = dict(conv3=nn.Conv2d(5, 7, 3), conv1=nn.Conv2d(12, 4, 1), lin=nn.Linear(6, 9), bn=nn.BatchNorm2d(10), emb=nn.Embedding(11, 8))
+    for m in mods.values():
+        m.apply(ref_utils.init_weight)
+    for k, m in mods.items():
+        out[f"init_{k}_weight"] = m.weight.detach().numpy()
+        if getattr(m, "bias", None) is not None:
+            out[f"init_{k}_bias"] = m.bias.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "aux.npz"), **out)
+    print("aux: done", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for name, args in CASES.items():
@@ -155,3 +182,5 @@ if __name__ == "__main__":
         gen_case(name, *args)
     if not only or "localpad" in only:
         localpad_case()
+    if not only or "aux" in only:
+        aux_case()

@@ -171,6 +171,56 @@ def test_full_width_configs_against_oracle(kw, th, tw):
         assert err <= TOL[precision]
 
 
+def test_device_noise_field_matches_philox_reference_and_decomposes():
+    """itg_noise_normal: Philox4x32-10 + Box-Muller on the device == the numpy restatement (tests/noise_ref.py, pinned on the Random123
+    known-answer vectors), windows of one field agree bit for bit, moments are those of a standard normal, and a Generator fed from
+    it produces the same band image as from the full field (what lets every rank draw only its own band)."""
+    import numpy as np
+    import noise_ref as NR
+    import infinite_texture_gans_b200 as itg
+    from infinite_texture_gans_b200 import bands
+    for c, k, o in NR.KAT:
+        assert tuple(int(v) for v in NR.philox4x32_10(*c, *k)) == o
+    full = itg.utils.noise_window((5, 37, 53), (0, 37, 0, 53), seed=0x1234567890ABCDEF, field=2, device="cuda")
+    ref = NR.noise_window((5, 37, 53), (0, 37, 0, 53), 0x1234567890ABCDEF, 2)
+    assert np.abs(full.cpu().numpy() - ref).max() <= 2e-5
+    win = itg.utils.noise_window((5, 37, 53), (9, 30, 7, 50), seed=0x1234567890ABCDEF, field=2, device="cuda")
+    assert torch.equal(win, full[:, 9:30, 7:50])
+    other = itg.utils.noise_window((5, 37, 53), (0, 37, 0, 53), seed=0x1234567890ABCDEF, field=3, device="cuda")
+    assert not torch.equal(other, full)
+    big = itg.utils.noise_window((16, 512, 512), (0, 512, 0, 512), seed=7, field=0, device="cuda")
+    assert abs(big.mean().item()) < 2e-3 and abs(big.std().item() - 1) < 2e-3 and abs((big ** 4).mean().item() - 3) < 5e-2
+    d, kw, ocfg, sd, z, maps = load_case("gen_ssm4_att_rep")
+    net = make_generator(kw, sd, "fp16", "cuda")
+    th, tw = 5, 4
+    zf, mf = itg.utils.draw_noise_device(net.cfg, th, tw, seed=99)
+    whole = itg.utils.generate_full_grid(net, zf.unsqueeze(0), [m[None, None] for m in mf]).clone()
+    zb, mb = itg.utils.draw_noise_device(net.cfg, th, tw, seed=99, rows=(2, 5))
+    zs, ms = bands.band_noise(net.cfg, zf, mf, 2, 5)
+    assert torch.equal(zb, zs) and all(torch.equal(a, b) for a, b in zip(mb, ms))
+    assert whole.shape[-2] == th * net.cfg.patch_px and torch.isfinite(whole).all()
+
+
+def test_replica_sharding_of_independent_textures():
+    """bands.generate_textures_replicas (config 4: independent textures, replicas only): rank r of `world` yields textures r, r + world, ...,
+    each equal to the blocking sampler's image for that noise."""
+    import infinite_texture_gans_b200 as itg
+    from infinite_texture_gans_b200 import bands
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn5_gamma0_rep")
+    net = make_generator(kw, sd, "fp16", "cuda")
+    H, W = int(d["H"]), int(d["W"])
+    g = torch.Generator().manual_seed(3)
+    noises = [(torch.randn(z.shape, generator=g), None) for _ in range(7)]
+    seen = {}
+    for rank in range(3):
+        for idx, img in bands.generate_textures_replicas(net, iter(noises), H, W, rank=rank, world=3):
+            seen[idx] = img.clone()
+    assert sorted(seen) == list(range(7))
+    for idx in (0, 4, 6):
+        want = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], output_resolution_height=H, output_resolution_width=W, noise=noises[idx])
+        assert torch.equal(seen[idx], want)
+
+
 def test_no_cpu_fallback():
     import infinite_texture_gans_b200 as itg
     d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
@@ -189,6 +239,7 @@ def test_two_gpu_band_split_equals_single_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "tools", "band_check.py"), "p2p"]
+    # (tools/band_check.py drives bands.RowBandSampler: the package's public multi-GPU sampler)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "max|bands - single GPU| = 0.000e+00" in r.stdout

@@ -206,3 +206,35 @@ def test_sequential_protocol_other_subimage_sizes(nps, H, W):
                                                       schedule="sequential", noise=(z, None))
     assert tuple(got.shape) == (1, 3, H, W)
     assert (got - ref).abs().max().item() <= 5e-5
+
+
+def test_build_z_build_maps_and_init_weight_match_the_reference():
+    """utils.build_z / utils.build_maps (utils.py:221-256) and layers.init_weight (utils.py:745-762) against outputs of the unmodified
+    reference under the same torch seeds (tests/golden/aux.npz, written by make_golden.py): same draw order, same overlapping
+    sub-image crops (stride (npw-1)*res, row-major), same initialisation scheme."""
+    import numpy as np
+    import torch.nn as nn
+    from common import GOLD
+    d = np.load(os.path.join(GOLD, "aux.npz"))
+    torch.manual_seed(71)
+    z = itg.utils.build_z(num_images=1, z_dim=6, base_res=4, num_patches_height=3, num_patches_width=3,
+                          total_num_patches_height=5, total_num_patches_width=7)
+    assert z.dtype == torch.float32 and torch.equal(z, torch.from_numpy(d["build_z"]))
+    torch.manual_seed(72)
+    maps = itg.utils.build_maps(num_images=1, map_dim=1, n_layers_G=3, base_res=4, num_patches_height=3, num_patches_width=3,
+                                total_num_patches_height=5, total_num_patches_width=7)
+    assert len(maps) == 3
+    for i, m in enumerate(maps):
+        assert torch.equal(m, torch.from_numpy(d[f"build_maps{i}"])), i
+    torch.manual_seed(73)
+    mods = dict(conv3=nn.Conv2d(5, 7, 3), conv1=nn.Conv2d(12, 4, 1), lin=nn.Linear(6, 9), bn=nn.BatchNorm2d(10), emb=nn.Embedding(11, 8))
+    for m in mods.values():
+        m.apply(itg.layers.init_weight)
+    for k, m in mods.items():
+        assert torch.equal(m.weight.detach(), torch.from_numpy(d[f"init_{k}_weight"])), k
+        if getattr(m, "bias", None) is not None:
+            assert torch.equal(m.bias.detach(), torch.from_numpy(d[f"init_{k}_bias"])), k
+    # properties the scheme guarantees (what BASELINE.json calls "random-init weights"): orthonormal rows or columns, zero biases
+    w = mods["conv3"].weight.detach().reshape(7, -1)
+    assert torch.allclose(w @ w.t(), torch.eye(7), atol=1e-5)
+    assert float(mods["conv3"].bias.detach().abs().max()) == 0.0 and abs(float(mods["bn"].weight.detach().mean()) - 1.0) < 0.05
