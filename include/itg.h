@@ -161,7 +161,10 @@ int itg_attention_fwd(int32_t dtype, const void* x, int32_t th, int32_t tw, int3
  *   x       : grid tensor to modulate, x_c storage channels, interior x_h x x_w, read at (y >> x_shift, x >> x_shift)
  *             (x_shift = 1: the nearest-2x up-sampling of generators.py:95-111 folded into the addressing)
  *   mean / rstd : [c] running_mean and 1/sqrt(running_var + eps) of the affine-free BatchNorm (layers.py:218)
- *   out     : grid tensor h x w x c, frame written per `border` */
+ *   out     : grid tensor h x w x c, frame written per `border`
+ *   zero_ring : 0 for the local-padding Generator (valid convs on over-sized noise maps, utils.py:237-256).  1 for the non-local Generator
+ *             (--padding_mode zeros: mlp_shared and embed are conv3x3(..., p=1), layers.py:213-224): the caller zero-extends the r x r map by
+ *             2 px and the kernel forces the hidden map to zero outside the image, which is what zero-padding embed's input means */
 typedef struct itg_ssm_desc {
   int32_t dtype;        /* ITG_F16 | ITG_BF16 */
   int32_t border;       /* itg_border applied to out's frame */
@@ -181,7 +184,7 @@ typedef struct itg_ssm_desc {
   const float* rstd;
   void* out;
   float leak;
-  int32_t reserved;
+  int32_t zero_ring;
 } itg_ssm_desc;
 int itg_ssm_desc_size(void);
 int itg_ssm_fwd(const itg_ssm_desc* desc, void* stream);

@@ -56,7 +56,7 @@ class SsmDesc(C.Structure):
         ("map", C.c_void_p), ("map_pitch", C.c_int32), ("x_shift", C.c_int32),
         ("w_mlp", C.c_void_p), ("w_embed", C.c_void_p), ("b_embed", C.c_void_p),
         ("x", C.c_void_p), ("x_c", C.c_int32), ("x_h", C.c_int32), ("x_w", C.c_int32), ("linear", C.c_int32),
-        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("out", C.c_void_p), ("leak", C.c_float), ("reserved", C.c_int32),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("out", C.c_void_p), ("leak", C.c_float), ("zero_ring", C.c_int32),
     ]
 
 

@@ -51,8 +51,6 @@ def main(argv=None) -> str:
     torch.serialization.add_safe_globals([argparse.Namespace])
     ckpt = torch.load(a.model_path, map_location="cpu", weights_only=not a.unsafe_load)
     args, sd = ckpt["args"], ckpt["netG_state_dict"]
-    if getattr(args, "padding_mode", "local") != "local":
-        raise SystemExit("only --padding_mode local checkpoints are supported (SURVEY 8f: the 'zeros' generator is out of scope)")
     netG = generators.ResidualPatchGenerator(
         z_dim=args.z_dim, G_ch=args.G_ch, base_res=args.base_res, n_layers_G=args.n_layers_G, attention=args.attention,
         img_ch=args.img_ch, leak=args.leak_G, SN=False, type_norm=args.type_norm_G, map_dim=1, padding_mode=args.padding_mode,
@@ -63,9 +61,16 @@ def main(argv=None) -> str:
     if a.seed is not None:
         torch.manual_seed(a.seed)
     with torch.no_grad():
-        img = utils.sample_from_gen_PatchByPatch_test(
-            netG, z_dim=args.z_dim, base_res=args.base_res, num_images=1, output_resolution_height=a.output_resolution_height,
-            output_resolution_width=a.output_resolution_width, device=device, schedule=a.schedule, return_on_device=True)
+        if args.padding_mode != "local":                 # test_sample.py:70-73: the non-local Generator, optionally tiled
+            scale = 2 ** (netG.n_layers_G - 1)
+            img = utils.sample_from_gen(netG, z_dim=args.z_dim, base_res=a.output_resolution_height // scale, num_images=1, tiles=a.tiles,
+                                        device=device)
+        else:
+            if a.tiles:
+                print("--tiles only applies to --padding_mode zeros checkpoints (test_sample.py:70-73); ignored for local padding")
+            img = utils.sample_from_gen_PatchByPatch_test(
+                netG, z_dim=args.z_dim, base_res=args.base_res, num_images=1, output_resolution_height=a.output_resolution_height,
+                output_resolution_width=a.output_resolution_width, device=device, schedule=a.schedule, return_on_device=True)
         # test_sample.py:78 `save_image(img * 0.5 + 0.5, path)`: torchvision quantises with mul(255).add_(0.5).clamp_(0, 255).to(uint8) and
         # hands the (H, W, C) bytes to PIL.  The same bytes are produced on the device (a quarter of the PCIe traffic of the fp32 image).
         arr = utils.image_to_uint8(img).cpu().numpy()

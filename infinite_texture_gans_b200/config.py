@@ -18,6 +18,7 @@ class GenConfig:
     type_norm: str = "BN"          # 'BN' | 'SSM'   (--type_norm_G, utils.py:69)
     map_dim: int = 1
     outer_padding: str = "replicate"   # 'replicate' | 'constant' ('zeros' is accepted as an alias)
+    padding_mode: str = "local"        # 'local' (patch grid, LocalPadder) | 'zeros' (the non-local Generator: whole image, zero-padded convs)
 
     def __post_init__(self):
         if self.n_layers_G not in (4, 5, 6):
@@ -26,6 +27,8 @@ class GenConfig:
             raise ValueError(f"type_norm must be 'BN' or 'SSM', got {self.type_norm!r}")
         if self.outer_padding not in ("replicate", "constant", "zeros"):
             raise ValueError(f"outer_padding must be 'replicate' or 'constant', got {self.outer_padding!r}")
+        if self.padding_mode not in ("local", "zeros"):
+            raise ValueError(f"padding_mode must be 'local' or 'zeros' (models/layers.py:19-27), got {self.padding_mode!r}")
         if self.map_dim != 1:
             raise ValueError("map_dim != 1 is not supported (test_sample.py:56 hard-codes map_dim=1)")
         if self.img_ch < 1 or self.img_ch > 8:
@@ -56,7 +59,11 @@ class GenConfig:
 
     @property
     def border_is_replicate(self) -> bool:
-        return self.outer_padding == "replicate"
+        return self.outer_padding == "replicate" and self.padding_mode == "local"     # zero-padded convs: the frame is zeros
+
+    @property
+    def nonlocal_mode(self) -> bool:
+        return self.padding_mode == "zeros"
 
 
 def flops_per_patch(cfg: GenConfig) -> float:

@@ -472,13 +472,15 @@ int launch_ssm(const itg_ssm_desc& d, cudaStream_t st) {
   p.map = d.map; p.map_pitch = d.map_pitch;
   p.w1 = d.w_mlp; p.w2 = d.w_embed;
   p.n_pad = d.n_pad;
+  p.zero_ring = d.zero_ring ? 1 : 0;
   const int sms = sm_count();
   static const int env_cg = getenv("ITG_SSM_CG") ? atoi(getenv("ITG_SSM_CG")) : 2;
   int cg = env_cg == 1 ? 1 : 2;
   // N blocking: the weights of one block (all taps, K = 128) stay in shared memory for the whole launch -- 64 columns per CTA
   if (cg == 2) {
     p.nblocks = (d.n_pad + itg::SSM2_NPAIR_MAX - 1) / itg::SSM2_NPAIR_MAX;
-    p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 31) / 32 * 32;            // per pair; each CTA parks n_blk / 2 columns
+    static const int n_gran = getenv("ITG_SSM_NGRAN") ? atoi(getenv("ITG_SSM_NGRAN")) : 32;     // developer sweep: N granularity of the pair MMA
+    p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + n_gran - 1) / n_gran * n_gran;   // per pair; each CTA parks n_blk / 2 columns
     if (p.nblocks > sms / 2) cg = 1;
   }
   if (cg == 1) {

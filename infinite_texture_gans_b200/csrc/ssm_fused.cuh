@@ -67,6 +67,7 @@ struct SsmParams {
   int n_pad, n_blk, nblocks;
   uint32_t idesc_mlp, idesc_emb;
   unsigned long long* dbg;  // optional cycle counters of CTA 0 (ITG_TILE_DBG=1)
+  int zero_ring;            // 1: hidden map forced to zero on the ring outside the image (non-local Generator, zero-padded convs)
   int exp;                  // developer experiments (ITG_SSM_EXP bit mask: WRONG RESULTS, timing only): 1 no proxy fence, 2 no plane stores,
                             // 4 no epilogue math / stores, 8 one tap per k-step
   EpiParams ep;
@@ -292,7 +293,17 @@ ssm_fused_kernel(const SsmParams p) {
     const uint32_t dst = sbase + SSM_OFF_A + (uint32_t)hp * 16u;
     unsigned long long dacc[3] = {0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
-    for (int it = 0; it < n_my; ++it) {
+    const int hy = hp / HALO_W, hx = hp - hy * HALO_W;
+    int tile = slot;
+    for (int it = 0; it < n_my; ++it, tile += nslots) {
+      // zero padding of the non-local Generator (--padding_mode zeros: conv3x3(..., p=1) of layers.py:213-224): the hidden map is zero
+      // OUTSIDE the image, i.e. on the outermost ring of the (h+2) x (w+2) valid-conv grid, instead of relu(conv(zero-extended map))
+      bool ring = false;
+      if (p.zero_ring) {
+        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int my = ty * TILE_H + hy, mx = tx * TILE_W + hx;
+        ring = my == 0 || mx == 0 || my >= p.h + 1 || mx >= p.w + 1;
+      }
       if (lane == 0) mbar_wait(bar_mlp_full, (uint32_t)it & 1u);
       __syncwarp();
       ITG_SACC(0, tl);
@@ -306,7 +317,7 @@ ssm_fused_kernel(const SsmParams p) {
       for (int g = 0; g < SSM_GROUPS; ++g) {
         uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
+        for (int i = 0; i < 16; ++i) w[i] = ring ? 0u : pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
         if (g + 1 < SSM_GROUPS) tmem_ld32_issue(trow + (uint32_t)(32 * (g + 1)), r);
         if (lane == 0) mbar_wait(bar_a_empty + 8 * g, ((uint32_t)it & 1u) ^ 1u);       // the previous tile's MMAs have read these planes
         __syncwarp();

@@ -302,7 +302,16 @@ ssm_fused2_kernel(const SsmParams p) {
     const uint32_t dst = sbase + SSM2_OFF_A + (uint32_t)hp * 16u;
     unsigned long long dacc[3] = {0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;
-    for (int it = 0; it < n_my; ++it) {
+    const int hy = hp / HALO_W, hx = hp - hy * HALO_W;
+    int pt = slot;
+    for (int it = 0; it < n_my; ++it, pt += nslots) {
+      bool ring = false;                              // non-local Generator: the hidden map is zero outside the image (see ssm_fused.cuh)
+      if (p.zero_ring) {
+        const int tile = 2 * pt + (int)rank;
+        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int my = ty * TILE_H + hy, mx = tx * TILE_W + hx;
+        ring = my == 0 || mx == 0 || my >= p.h + 1 || mx >= p.w + 1;
+      }
       if (lane == 0) mbar_wait_cluster(bar_mlp_full, (uint32_t)it & 1u);
       __syncwarp();
       ITG_SACC(0, tl);
@@ -316,7 +325,7 @@ ssm_fused2_kernel(const SsmParams p) {
       for (int g = 0; g < SSM_GROUPS; ++g) {
         uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
+        for (int i = 0; i < 16; ++i) w[i] = ring ? 0u : pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
         if (g + 1 < SSM_GROUPS) tmem_ld32_issue(trow + (uint32_t)(32 * (g + 1)), r);
         if (lane == 0) mbar_wait_cluster(bar_a_empty + 8 * g, ((uint32_t)it & 1u) ^ 1u);
         __syncwarp();

@@ -175,11 +175,15 @@ class Plan:
         b = cfg.base_res
         P = cfg.patch_px
         # static inputs / outputs (caller copies into / out of them; stable addresses for CUDA graphs)
-        self.z_in = torch.empty((cfg.z_dim, th * b + 2, tw * b + 2), dtype=torch.float32, device=device)
+        # (non-local Generator: the rings stay zero -- they ARE the zero padding of start / mlp_shared -- and set_inputs fills the interiors)
+        alloc = torch.zeros if cfg.nonlocal_mode else torch.empty
+        self.z_in = alloc((cfg.z_dim, th * b + 2, tw * b + 2), dtype=torch.float32, device=device)
         self.maps_in: List[torch.Tensor] = []
         if cfg.type_norm == "SSM":
-            self.maps_in = [torch.empty((th * cfg.level_res(k) + 4, tw * cfg.level_res(k) + 4), dtype=torch.float32,
-                                        device=device) for k in range(1, cfg.n_layers_G + 1)]
+            self.maps_in = [alloc((th * cfg.level_res(k) + 4, tw * cfg.level_res(k) + 4), dtype=torch.float32,
+                                  device=device) for k in range(1, cfg.n_layers_G + 1)]
+            if cfg.nonlocal_mode and not self.fuse_ssm:
+                raise NotImplementedError("the non-local SSM Generator runs on the fused 16-bit kernel only (precision 'fp16' / 'bf16')")
         if img_layout == L.IMG_MERGED:
             self.out = torch.empty((1, cfg.img_ch, th * P, tw * P), dtype=torch.float32, device=device)
         else:
@@ -246,6 +250,10 @@ class Plan:
                                          out_c=None, img=True)))
 
     def _attention(self, x: _VGrid, out_raw: Optional[_VGrid], out_act: Optional[_VGrid], norm: Optional[str]):
+        if self.cfg.nonlocal_mode and not (x.h == x.w and x.h in (8, 16)):
+            raise NotImplementedError(
+                f"non-local Generator with attention over a {x.h}x{x.w} feature map: the attention kernel serves one 8x8 or 16x16 map "
+                "(z of 2x2 or 4x4, the sizes sample_from_gen(base_res=4) uses); larger maps need attention=False")
         self._touch(x, out_raw, out_act)
         self._steps.append(("att", dict(x=x, out_raw=out_raw, out_act=out_act, norm=norm)))
 
@@ -424,7 +432,7 @@ class Plan:
                 pre = a["prefix"]
                 op = SsmOp(map=self.maps_in[a["level"]], w_mlp=w[pre + "mlp.wf"], w_embed=w[pre + "embed.w"], b_embed=w[pre + "embed.b"],
                            x=a["x"].grid, x_shift=a["x_shift"], mean=w[pre + "mean"], rstd=w[pre + "rstd"], out=a["out"].grid,
-                           leak=self.cfg.leak, linear=a["linear"], border=a["border"], name=pre + "ssm")
+                           leak=self.cfg.leak, linear=a["linear"], border=a["border"], zero_ring=self.cfg.nonlocal_mode, name=pre + "ssm")
                 self.ops.append(("ssm", op))
                 self.fns.append(be.compile_ssm(op))
             else:
@@ -477,8 +485,11 @@ class Plan:
     def _attention_op(self, a: dict) -> AttentionOp:
         cfg, w = self.cfg, self.w
         scale, shift = self._norm_vectors(a["norm"])
+        th, tw, patch = self.th, self.tw, cfg.level_res(3)
+        if cfg.nonlocal_mode:                      # the non-local Generator attends over the WHOLE feature map (layers.py:246-258 on the full image)
+            th, tw, patch = 1, 1, a["x"].h
         return AttentionOp(
-            x=a["x"].grid, th=self.th, tw=self.tw, patch=cfg.level_res(3), C=2 * cfg.G_ch,
+            x=a["x"].grid, th=th, tw=tw, patch=patch, C=2 * cfg.G_ch,
             w_theta=w["attention.theta.w"], b_theta=w["attention.theta.b"], w_phi=w["attention.phi.w"],
             b_phi=w["attention.phi.b"], w_g=w["attention.g.w"], b_g=w["attention.g.b"], w_o=w["attention.o.w"],
             b_o=w["attention.o.b"], gamma=w["attention.gamma"],
@@ -508,6 +519,8 @@ class Plan:
 
     def set_inputs(self, z: torch.Tensor, maps: Optional[Sequence[torch.Tensor]] = None) -> None:
         """Copy host- or device-resident fp32 noise into the plan's static input buffers (async on the current stream)."""
+        if self.cfg.nonlocal_mode:
+            return self._set_inputs_nonlocal(z, maps)
         z = z.reshape(self.z_in.shape) if z.dim() == 4 else z
         if tuple(z.shape) != tuple(self.z_in.shape):
             raise ValueError(f"z has shape {tuple(z.shape)}, the {self.th}x{self.tw} patch grid needs {tuple(self.z_in.shape)}")
@@ -522,6 +535,24 @@ class Plan:
                 dst.copy_(m, non_blocking=True)
 
 
+    def _set_inputs_nonlocal(self, z: torch.Tensor, maps: Optional[Sequence[torch.Tensor]]) -> None:
+        """Non-local Generator (sample_from_gen, utils.py:530-575): z is the bare (z_dim, h, w) latent and the maps are r x r; the zero rings
+        of the static buffers are the zero padding of the first convs."""
+        z = z[0] if z.dim() == 4 else z
+        want = (self.cfg.z_dim, self.z_in.shape[1] - 2, self.z_in.shape[2] - 2)
+        if tuple(z.shape) != want:
+            raise ValueError(f"z has shape {tuple(z.shape)}, this plan needs {want}")
+        self.z_in[:, 1:-1, 1:-1].copy_(z, non_blocking=True)
+        if self.cfg.type_norm == "SSM":
+            if maps is None or len(maps) < len(self.maps_in):
+                raise ValueError("SSM Generator needs one noise map per level (utils.py:558-564)")
+            for dst, m in zip(self.maps_in, maps):
+                m = m.reshape(m.shape[-2], m.shape[-1])
+                if (m.shape[0] + 4, m.shape[1] + 4) != tuple(dst.shape):
+                    raise ValueError(f"map has shape {tuple(m.shape)}, expected {(dst.shape[0] - 4, dst.shape[1] - 4)}")
+                dst[2:-2, 2:-2].copy_(m, non_blocking=True)
+
+
 class Engine:
     """Packed weights + cached plans (+ optional CUDA graphs) of one Generator."""
 
@@ -529,6 +560,11 @@ class Engine:
                  backend=None):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        if cfg.nonlocal_mode:
+            # the non-local Generator is fully convolutional over the whole image: plans address the h x w latent grid as an h x w grid
+            # of 1-pixel "patches" (base_res 1) with a zero frame
+            import dataclasses
+            cfg = dataclasses.replace(cfg, base_res=1)
         self.cfg, self.precision = cfg, precision
         self.dtype, self.impl = PRECISIONS[precision]
         self.device = torch.device(device)

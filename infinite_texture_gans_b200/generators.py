@@ -32,9 +32,8 @@ class ResidualPatchGenerator(nn.Module):
                  type_norm="BN", map_dim=1, padding_mode="local", outer_padding="replicate", num_patches_h=3,
                  num_patches_w=3, padding_size=1, conv_reduction=2, precision="fp16"):
         super().__init__()
-        if padding_mode != "local":
-            raise NotImplementedError("only --padding_mode local is implemented (the 'zeros' generator is the "
-                                      "non-local path, out of scope: SURVEY 8f)")
+        if padding_mode not in ("local", "zeros"):
+            raise ValueError("padding_mode must be 'local' or 'zeros' (models/layers.py:19-27)")
         if SN:
             raise NotImplementedError("spectral-norm checkpoints are not loadable by test_sample.py either (SN=False, :56)")
         self.z_dim, self.base_ch, self.base_res, self.n_layers_G = z_dim, G_ch, base_res, n_layers_G
@@ -45,7 +44,7 @@ class ResidualPatchGenerator(nn.Module):
         self.precision = precision
         self.cfg = GenConfig(z_dim=z_dim, G_ch=G_ch, base_res=base_res, n_layers_G=n_layers_G, attention=bool(attention),
                              img_ch=img_ch, leak=float(leak), type_norm=type_norm, map_dim=map_dim,
-                             outer_padding="constant" if outer_padding == "zeros" else outer_padding)
+                             outer_padding="constant" if outer_padding == "zeros" else outer_padding, padding_mode=padding_mode)
         # class-level, like the reference (models/generators.py:49-50)
         LocalPadder.set_attributes(num_patches_h=num_patches_h, num_patches_w=num_patches_w, outer_padding=outer_padding,
                                    padding_size=padding_size, conv_reduction=conv_reduction)
@@ -103,6 +102,8 @@ class ResidualPatchGenerator(nn.Module):
         (N, 1, nph*r+4, npw*r+4) map.  Returns (N*nph*npw, img_ch, P, P) fp32 patches, row-major."""
         if self.training:
             raise NotImplementedError("training-mode forward (batch statistics, autograd) is out of scope: call .eval()")
+        if self.padding_mode == "zeros":
+            return self._forward_nonlocal(z, maps)
         nph, npw = LocalPadder.num_patches_h, LocalPadder.num_patches_w
         cfg, b = self.cfg, self.cfg.base_res
         if z.dim() != 4 or z.shape[1] != cfg.z_dim or z.shape[2] != nph * b + 2 or z.shape[3] != npw * b + 2:
@@ -137,5 +138,29 @@ class ResidualPatchGenerator(nn.Module):
             with eng._on_device():                    # launches go to the current stream of the engine's device
                 plan.set_inputs(z[n].float(), mp)
                 plan.run(self._seq.hooks(plan, image_location) if N == 1 else None)
+                outs.append(plan.out.clone())
+        return outs[0] if N == 1 else torch.cat(outs, 0)
+
+    def _forward_nonlocal(self, z, maps=None):
+        """The non-local Generator (--padding_mode zeros, models/layers.py:19-27: every conv is conv3x3(..., p=1) on the whole image, no
+        LocalPadder, image_location ignored): z (N, z_dim, h, w) -> (N, img_ch, h * 2^(n-1), w * 2^(n-1)); maps (SSM): per level
+        (N, 1, h * 2^i, w * 2^i) (utils.sample_from_gen, utils.py:530-575).  Same kernels as the local path with a zero frame; the latent
+        grid of h x w pixels plays the role of the patch grid.  Attention (over the whole level-3 map) is served for 8x8 / 16x16 maps."""
+        cfg = self.cfg
+        if z.dim() != 4 or z.shape[1] != cfg.z_dim:
+            raise ValueError(f"z must be (N, {cfg.z_dim}, h, w), got {tuple(z.shape)}")
+        N, _, h, w = z.shape
+        eng = self.engine()
+        plan = eng.plan(h, w, L.IMG_MERGED)
+        outs: List[torch.Tensor] = []
+        for n in range(N):
+            mp = None
+            if cfg.type_norm == "SSM":
+                if maps is None or maps[0] is None:
+                    raise ValueError("type_norm='SSM' needs the per-level noise maps (utils.py:558-564)")
+                mp = [maps[i][n, 0].float() for i in range(cfg.n_layers_G)]
+            with eng._on_device():
+                plan.set_inputs(z[n].float(), mp)
+                plan.run()
                 outs.append(plan.out.clone())
         return outs[0] if N == 1 else torch.cat(outs, 0)

@@ -152,6 +152,7 @@ class SsmOp:
     leak: float = 0.0
     linear: bool = False
     border: int = L.BORDER_NONE
+    zero_ring: bool = False            # non-local Generator: hidden map zero outside the image
     name: str = "ssm"
 
 
@@ -222,6 +223,7 @@ class CudaBackend:
         d.w_mlp, d.w_embed, d.b_embed = L.ptr(op.w_mlp), L.ptr(op.w_embed), L.ptr(op.b_embed)
         d.x, d.x_c, d.x_h, d.x_w, d.linear = L.ptr(op.x.buf), op.x.c, op.x.h, op.x.w, int(op.linear)
         d.mean, d.rstd, d.out, d.leak = L.ptr(op.mean), L.ptr(op.rstd), L.ptr(out.buf), float(op.leak)
+        d.zero_ring = int(op.zero_ring)
         fn, name = self.lib.itg_ssm_fwd, op.name
 
         def launch():

@@ -230,6 +230,50 @@ def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, nu
     return img if return_on_device else img.cpu()
 
 
+def tile_process(img: torch.Tensor, model, scale: int = 4, tile_size: int = 32, tile_pad: int = 8) -> torch.Tensor:
+    """utils.tile_process (utils.py:401-470): run `model` on overlapping tiles of the latent `img` (N, C, h, w) and paste the centres
+    into the (N, 3, h*scale, w*scale) output.  Same tiling arithmetic; the output stays on the device of the tiles."""
+    from math import ceil as _ceil
+    batch, _, height, width = img.shape
+    out = None
+    tiles_x, tiles_y = _ceil(width / tile_size), _ceil(height / tile_size)
+    for y in range(tiles_y):
+        for x in range(tiles_x):
+            x0, y0 = x * tile_size, y * tile_size
+            x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
+            x0p, x1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width)
+            y0p, y1p = max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
+            tile = model(img[:, :, y0p:y1p, x0p:x1p])
+            if out is None:
+                out = tile.new_zeros((batch, tile.shape[1], height * scale, width * scale))
+            ox, oy = (x0 - x0p) * scale, (y0 - y0p) * scale
+            out[:, :, y0 * scale:y1 * scale, x0 * scale:x1 * scale] = tile[:, :, oy:oy + (y1 - y0) * scale, ox:ox + (x1 - x0) * scale]
+    return out
+
+
+def sample_from_gen(netG, z_dim=128, base_res=4, map_dim=1, num_images=1, tiles=False, device="cpu", noise=None):
+    """utils.sample_from_gen (utils.py:530-575): the sampler of the NON-local Generator (--padding_mode zeros): z ~ N(0, 1) of
+    (num_images, z_dim, base_res, base_res), per-level SSM maps of (num_images, 1, r, r), one forward -- or, with tiles=True,
+    `tile_process(z, netG, 2^(n-1), 32, 16)` (test_sample.py:70-73).  Same draw order on the host RNG as the reference.
+    noise: optional (z, maps) to use instead of drawing."""
+    G = _unwrap(netG)
+    n_layers_G, type_norm = G.n_layers_G, G.type_norm
+    if noise is None:
+        z = torch.randn(num_images, z_dim, base_res, base_res)
+        maps = None
+        if type_norm == "SSM":
+            maps = [torch.randn(num_images, map_dim, base_res * 2 ** i, base_res * 2 ** i) for i in range(n_layers_G)]
+    else:
+        z, maps = noise
+    if maps is None:
+        maps = [None] * n_layers_G
+    if tiles:
+        if type_norm == "SSM":
+            raise ValueError("tile_process feeds the model the latent only (utils.py:443): SSM Generators cannot be tiled")
+        return tile_process(z, netG, 2 ** (n_layers_G - 1), 32, 16)
+    return netG(z, maps, image_location="1st_row_1st_col")
+
+
 # ------------------------------------------------------------------------------------------------
 # output stage
 # ------------------------------------------------------------------------------------------------

@@ -435,6 +435,67 @@ def forward_merged(sd, cfg: GenCfg, z_full: Tensor, maps_full: Optional[Sequence
     return h if pre_tanh else torch.tanh(h)
 
 
+# --------------------------------------------------------------------------------------------
+# The non-local Generator (--padding_mode zeros): every conv is zero-padded, no patch structure
+# --------------------------------------------------------------------------------------------
+def _ssm_zeros(x: Tensor, m: Tensor, sd, prefix: str) -> Tensor:
+    """StochasticSpatialModulation.forward with padding_mode='zeros' (p = 1 for mlp_shared and embed, models/layers.py:213-224):
+    x (B,C,r,r), m (B,1,r,r)."""
+    out = _bn_eval(x, sd, prefix + "bn.", affine=False)
+    actv = F.relu(_conv(m.to(x.dtype), sd, prefix + "mlp_shared.0.", padding=1))
+    emb = _conv(actv, sd, prefix + "embed.", padding=1)
+    gamma, beta = emb.chunk(2, dim=1)
+    return (1 + gamma) * out + beta
+
+
+def forward_nonlocal(sd, cfg: GenCfg, z: Tensor, maps: Optional[Sequence[Tensor]] = None, pre_tanh: bool = False) -> Tensor:
+    """ResidualPatchGenerator.forward (models/generators.py:86-124) built with padding_mode='zeros' (conv2d_lp -> conv3x3(..., p=1),
+    models/layers.py:26-27): z (N,z_dim,h,w) -> (N,img_ch,h*2^(n-1),w*2^(n-1)); attention over the whole level-3 map."""
+    maps = list(maps) if maps is not None else [None] * cfg.n_layers_G
+    ssm_mode = cfg.type_norm == "SSM"
+
+    def norm(x, m, prefix):
+        return _ssm_zeros(x, m, sd, prefix) if ssm_mode else _bn_eval(x, sd, prefix)
+
+    h = _conv(z, sd, "start.conv.", padding=1)
+    for k, (cin, cout) in enumerate(cfg.block_channels(), start=1):
+        if k > 1:
+            h = F.interpolate(h, scale_factor=2, mode="nearest")
+        m = maps[k - 1]
+        pre = f"block{k}."
+        t = _conv(_act(norm(h, m, pre + "bn1."), cfg.leak), sd, pre + "conv1.conv.", padding=1)
+        t = _conv(_act(norm(t, m, pre + "bn2."), cfg.leak), sd, pre + "conv2.conv.", padding=1)
+        sc = h
+        if cin != cout:
+            if ssm_mode:
+                sc = _ssm_zeros(sc, m, sd, pre + "bn3.")
+            sc = _conv(sc, sd, pre + "conv3.")
+        h = t + sc
+        if k == 3 and cfg.attention:
+            h = attention(h, sd)
+    if not ssm_mode:
+        h = _bn_eval(h, sd, "bn.")
+    h = _conv(_act(h, cfg.leak), sd, "final.conv.", padding=1)
+    return h if pre_tanh else torch.tanh(h)
+
+
+def tile_process(z: Tensor, model, scale: int, tile_size: int = 32, tile_pad: int = 8) -> Tensor:
+    """utils.tile_process (utils.py:401-470): overlapping latent tiles, centres pasted into the output."""
+    n, _, height, width = z.shape
+    out = None
+    for y in range(math.ceil(height / tile_size)):
+        for x in range(math.ceil(width / tile_size)):
+            x0, y0 = x * tile_size, y * tile_size
+            x1, y1 = min(x0 + tile_size, width), min(y0 + tile_size, height)
+            x0p, x1p, y0p, y1p = max(x0 - tile_pad, 0), min(x1 + tile_pad, width), max(y0 - tile_pad, 0), min(y1 + tile_pad, height)
+            t = model(z[:, :, y0p:y1p, x0p:x1p])
+            if out is None:
+                out = t.new_zeros((n, t.shape[1], height * scale, width * scale))
+            ox, oy = (x0 - x0p) * scale, (y0 - y0p) * scale
+            out[:, :, y0 * scale:y1 * scale, x0 * scale:x1 * scale] = t[:, :, oy:oy + (y1 - y0) * scale, ox:ox + (x1 - x0) * scale]
+    return out
+
+
 def image_to_patches(img: Tensor, P: int) -> Tensor:
     """(1,C,th*P,tw*P) -> (th*tw,C,P,P), row-major patch order (the Generator's return layout)."""
     return crop_windows(img, P, P, P)

@@ -55,3 +55,22 @@ def compare_with_golden(d, key, img: torch.Tensor, atol: float, H=None, W=None):
         err = (img[:, :, ::3, ::3] - ref).abs().max().item()
     assert err <= atol, f"{key}: max-abs {err:.3e} > {atol:g}"
     return err
+
+
+NONLOCAL_CASES = ("bn4_att_b4", "bn5_noatt_b11", "ssm4_noatt_b6", "bn4_noatt_tiles_b40")
+
+
+def load_nonlocal_case(name):
+    """tests/golden/nonlocal.npz (reference utils.sample_from_gen with padding_mode='zeros') -> (golden image, kwargs, oracle cfg, weights,
+    z, maps, tiles): the noise is re-drawn in the reference's order (utils.py:549, 562) from the stored seed."""
+    d = np.load(os.path.join(GOLD, "nonlocal.npz"))
+    kw = ast.literal_eval(str(d[name + "_cfg"]))
+    b, tiles, wseed, nseed = (int(v) for v in d[name + "_args"])
+    ocfg = O.GenCfg(**kw)
+    sd = O.make_state_dict(ocfg, wseed, stress=True)
+    torch.manual_seed(nseed)
+    z = torch.randn(1, kw["z_dim"], b, b)
+    maps = None
+    if kw["type_norm"] == "SSM":
+        maps = [torch.randn(1, 1, b * 2 ** i, b * 2 ** i) for i in range(kw["n_layers_G"])]
+    return torch.from_numpy(d[name + "_img"]), kw, ocfg, sd, z, maps, bool(tiles)

@@ -149,6 +149,8 @@ class EmulatorBackend:
         w1 = op.w_mlp.float()                                               # [128, 16]
         taps = torch.stack([m[t // 3:t // 3 + H + 2, t % 3:t % 3 + W + 2] for t in range(9)], -1)      # (H+2, W+2, 9)
         m1 = torch.relu(taps @ w1[:, :9].t() + (w1[:, 9] + w1[:, 10])).to(dt).float()                    # (H+2, W+2, 128)
+        if op.zero_ring:                                                    # zero padding of embed's input (non-local Generator)
+            m1[0], m1[-1], m1[:, 0], m1[:, -1] = 0, 0, 0, 0
         we = op.w_embed.float()                                             # [9, n_pad, 128]
         v = sum(m1[t // 3:t // 3 + H, t % 3:t % 3 + W] @ we[t].t() for t in range(9)) + op.b_embed.float()
         gamma, beta = v[..., 0:2 * C:2], v[..., 1:2 * C:2]

@@ -15,6 +15,7 @@ Fixtures:
                   'seq'  = utils.sample_from_gen_PatchByPatch_test (utils.py:258-397), 3x3 sub-image stepping
                   'one'  = one forward with LocalPadder.set_attributes(total_h,total_w) (the train-time call,
                            utils.py:475-527), merged with utils.merge_patches_into_image
+  nonlocal.npz -- utils.sample_from_gen outputs of the non-local Generator (padding_mode='zeros'), plain and with tile_process.
   aux.npz      -- utils.build_z / utils.build_maps outputs (utils.py:221-256) and utils.init_weight results (utils.py:745-762)
                   under fixed seeds: pins the host-side noise plumbing and the "random-init weights" scheme.
   localpad.npz -- integer-coded tensors pushed through models.layers.LocalPadder in eval mode for a whole
@@ -149,6 +150,35 @@ def localpad_case():
     print("localpad: done")
 
 
+def nonlocal_cases():
+    """The non-local Generator (padding_mode='zeros') through utils.sample_from_gen (utils.py:530-575), plain and tiled
+    (utils.tile_process, utils.py:401-470), and test_sample.py's base_res arithmetic (test_sample.py:70-73)."""
+    out = {}
+    cases = {
+        # name: (cfg kwargs, base_res passed to sample_from_gen, tiles, weight seed, noise seed)
+        "bn4_att_b4": (dict(z_dim=16, G_ch=8, n_layers_G=4, attention=True, leak=0.02, type_norm="BN", outer_padding="replicate"), 4, False, 81, 82),
+        "bn5_noatt_b11": (dict(z_dim=16, G_ch=8, n_layers_G=5, attention=False, leak=0.0, type_norm="BN", outer_padding="replicate"), 11, False, 83, 84),
+        "ssm4_noatt_b6": (dict(z_dim=16, G_ch=8, n_layers_G=4, attention=False, leak=0.02, type_norm="SSM", outer_padding="replicate"), 6, False, 85, 86),
+        "bn4_noatt_tiles_b40": (dict(z_dim=16, G_ch=8, n_layers_G=4, attention=False, leak=0.02, type_norm="BN", outer_padding="replicate"), 40, True, 87, 88),
+    }
+    for name, (kw, b, tiles, wseed, nseed) in cases.items():
+        cfg = O.GenCfg(**kw)
+        sd = O.make_state_dict(cfg, wseed, stress=True)
+        net = ref_gen.ResidualPatchGenerator(
+            z_dim=cfg.z_dim, G_ch=cfg.G_ch, base_res=cfg.base_res, n_layers_G=cfg.n_layers_G, attention=cfg.attention, img_ch=cfg.img_ch,
+            leak=cfg.leak, SN=False, type_norm=cfg.type_norm, map_dim=1, padding_mode="zeros", outer_padding=cfg.outer_padding)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        torch.manual_seed(nseed)
+        with torch.no_grad():
+            img = ref_utils.sample_from_gen(net, z_dim=cfg.z_dim, base_res=b, num_images=1, tiles=tiles, device="cpu")
+        out[name + "_cfg"] = np.array(repr(kw))
+        out[name + "_args"] = np.array([b, int(tiles), wseed, nseed])
+        out[name + "_img"] = img.numpy().astype(np.float32)
+        print(f"nonlocal {name}: {tuple(img.shape)}")
+    np.savez_compressed(os.path.join(HERE, "nonlocal.npz"), **out)
+
+
 def aux_case():
     """build_z / build_maps (noise draw + overlapping sub-image crops) and init_weight, straight from the reference."""
     import torch.nn as nn
@@ -184,3 +214,5 @@ if __name__ == "__main__":
         localpad_case()
     if not only or "aux" in only:
         aux_case()
+    if not only or "nonlocal" in only:
+        nonlocal_cases()

@@ -221,6 +221,30 @@ def test_replica_sharding_of_independent_textures():
         assert torch.equal(seen[idx], want)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["bn4_att_b4", "bn5_noatt_b11", "ssm4_noatt_b6", "bn4_noatt_tiles_b40"])
+def test_nonlocal_generator_matches_reference(name, precision):
+    """--padding_mode zeros (non-local Generator; test_sample.py:70-73, utils.py:401-470,530-575) on the CUDA path against the reference's
+    utils.sample_from_gen outputs: whole-image zero-padded convs, whole-map attention at 16x16, SSM with the hidden map zeroed outside the
+    image (fused 16-bit kernel), tile_process."""
+    import infinite_texture_gans_b200 as itg
+    from common import load_nonlocal_case
+    gold, kw, ocfg, sd, z, maps, tiles = load_nonlocal_case(name)
+    if kw["type_norm"] == "SSM" and precision == "fp32":
+        with pytest.raises(NotImplementedError):
+            net = itg.ResidualPatchGenerator(**kw, padding_mode="zeros", precision=precision)
+            net.load_state_dict(sd)
+            itg.utils.sample_from_gen(net.cuda().eval(), z_dim=kw["z_dim"], base_res=z.shape[-1], noise=(z, maps))
+        return
+    net = itg.ResidualPatchGenerator(**kw, padding_mode="zeros", precision=precision)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    img = itg.utils.sample_from_gen(net, z_dim=kw["z_dim"], base_res=z.shape[-1], tiles=tiles, noise=(z, maps)).cpu()
+    err = (img - gold).abs().max().item()
+    print(f"nonlocal {name} {precision}: max-abs {err:.3e}")
+    assert tuple(img.shape) == tuple(gold.shape) and err <= TOL[precision]
+
+
 def test_no_cpu_fallback():
     import infinite_texture_gans_b200 as itg
     d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")

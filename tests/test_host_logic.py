@@ -238,3 +238,32 @@ def test_build_z_build_maps_and_init_weight_match_the_reference():
     w = mods["conv3"].weight.detach().reshape(7, -1)
     assert torch.allclose(w @ w.t(), torch.eye(7), atol=1e-5)
     assert float(mods["conv3"].bias.detach().abs().max()) == 0.0 and abs(float(mods["bn"].weight.detach().mean()) - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("name,precision,tol", [("bn4_att_b4", "fp32", 5e-5), ("bn5_noatt_b11", "fp32", 5e-5), ("bn4_noatt_tiles_b40", "fp32", 5e-5),
+                                                ("ssm4_noatt_b6", "fp16", 2e-2)])
+def test_nonlocal_generator_and_sampler(name, precision, tol):
+    """--padding_mode zeros (the non-local Generator, test_sample.py:70-73): same launch plans with a zero frame; utils.sample_from_gen
+    and utils.tile_process mirror utils.py:401-470,530-575.  Checked (emulated launches) against the reference's golden outputs."""
+    from common import load_nonlocal_case
+    gold, kw, ocfg, sd, z, maps, tiles = load_nonlocal_case(name)
+    net = itg.ResidualPatchGenerator(**kw, padding_mode="zeros", precision=precision)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    net._test_backend = EmulatorBackend()
+    img = itg.utils.sample_from_gen(net, z_dim=kw["z_dim"], base_res=z.shape[-1], tiles=tiles, noise=(z, maps))
+    assert tuple(img.shape) == tuple(gold.shape)
+    assert (img.float() - gold).abs().max().item() <= tol
+
+
+def test_nonlocal_limits_are_reported():
+    from common import load_nonlocal_case
+    gold, kw, ocfg, sd, z, maps, tiles = load_nonlocal_case("bn4_att_b4")
+    net = itg.ResidualPatchGenerator(**kw, padding_mode="zeros", precision="fp32")
+    net.load_state_dict(sd)
+    net.eval()
+    net._test_backend = EmulatorBackend()
+    with pytest.raises(NotImplementedError, match="attention"):
+        net(torch.zeros(1, kw["z_dim"], 6, 6))                       # attention over a 24x24 map is not served
+    with pytest.raises(ValueError, match="padding_mode"):
+        itg.ResidualPatchGenerator(**kw, padding_mode="reflect")
