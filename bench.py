@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the patch-by-patch Generator inference path (BASELINE.json: output megapixels/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|cfg4|cfg5band] [--precision fp16|bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|cfg4|cfg5band] [--precision fp16|fp32]
     python bench.py --impl reference ...        # the reference algorithm's CPU path (oracle port) on the host cores
 
 One "step" = one Generator pass over one synthetic texture of the workload (random-init weights of the named
@@ -413,7 +413,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
                     help="default: the headline workload (" + HEADLINE + ") plus the other single-GPU BASELINE configs in `extra`")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo rows over peer-mapped memory (NVLink P2P) or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -473,7 +473,7 @@ def main():
         e = main_entry
         line = {"metric": "output megapixels/sec (Generator, local padding)", "value": e["value"], "unit": "MP/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": e["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision],
+                "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32"}[args.precision],
                 "data": "synthetic", "config": e["config"], "clocks": e["clocks"], "gpu_launches": e["gpu_launches"] + sum(x["gpu_launches"] for x in extras),
                 "e2e": e["e2e"], "roofline": e["roofline"], "parity": e["parity"]}
         if "cpu_baseline" in e:

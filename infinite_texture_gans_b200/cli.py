@@ -20,7 +20,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--model_path", type=str, default="results/241_lp_bn_outerpadRepl/300__ema.pth", help="path of the generator network")
     p.add_argument("--tiles", default=False, action="store_true", help="use tiling of the input (only read on the non-local path, test_sample.py:70-73)")
     # additions
-    p.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"], help="operand precision of the CUDA path")
+    p.add_argument("--precision", default="fp16", choices=["fp16", "fp32"], help="operand precision of the CUDA path (16-bit tensor-core mode / fp32 exact mode)")
     p.add_argument("--schedule", default="auto", choices=["auto", "oneshot", "sequential"],
                    help="oneshot: whole patch grid in one device-resident pass; sequential: the shipped 3x3 sub-image schedule; "
                         "auto: sequential iff the attention block contributes (gamma != 0), i.e. whenever the two differ")

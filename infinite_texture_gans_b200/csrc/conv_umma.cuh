@@ -68,8 +68,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #ifndef ITG_MBAR_TIMEOUT_CYCLES
 #define ITG_MBAR_TIMEOUT_CYCLES 4000000000LL      // ~2 s
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// The slow path is a real function call: inlined at every wait site it put a clock read, a printf call and a trap (~40 instructions) into
+// each hot loop, and the kernels' code outgrew the instruction caches (ncu: `no_instruction` was the top stall of the SSM kernel).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   // bounded: a broken pipeline traps instead of hanging the GPU.  Both a cycle budget and a poll budget must be exhausted:
   // a profiler that freezes the SM for seconds (ncu PM-sampling passes) advances the clock but not the polls.
   const long long t0 = clock64();
@@ -81,6 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;          // (one hardware-suspended retry before paying for the call)
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");

@@ -73,7 +73,12 @@ struct SsmParams {
   EpiParams ep;
 };
 
+// per-role cycle counters: compiled in only with -DITG_SSM_DBG (they cost code size in every hot loop)
+#ifdef ITG_SSM_DBG
 #define ITG_SACC(slot, tvar) do { if (p.dbg) { const long long now_ = clock64(); dacc[slot] += (unsigned long long)(now_ - tvar); tvar = now_; } } while (0)
+#else
+#define ITG_SACC(slot, tvar) do { (void)tvar; } while (0)
+#endif
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -255,7 +260,7 @@ ssm_fused_kernel(const SsmParams p) {
       __syncwarp();
       ITG_SACC(1, tl);
       const uint32_t d = tmem_base + (uint32_t)(b * p.n_blk);
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < SSM_GROUPS; ++g) {
         if (lane == 0) mbar_wait(bar_a_full + 8 * g, (uint32_t)it & 1u);
         __syncwarp();
@@ -313,7 +318,7 @@ ssm_fused_kernel(const SsmParams p) {
       uint32_t r[32];
       tmem_ld32_issue(trow, r);
       tmem_ld_wait(r);
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < SSM_GROUPS; ++g) {
         uint32_t w[16];
 #pragma unroll

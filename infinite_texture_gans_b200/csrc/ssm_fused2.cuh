@@ -79,28 +79,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       ::"r"(bar), "r"(cta)
       : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  unsigned polls = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++polls > (1u << 20) && clock64() - t0 > ITG_MBAR_TIMEOUT_CYCLES) {
-      printf("itg: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
+// (waits use mbar_wait: the default CTA-scope acquire on the local barrier, as CUTLASS's ClusterBarrier::wait does)
 
 template <typename T>
 __global__ void __launch_bounds__(SSM_THREADS, 1)
@@ -197,7 +176,7 @@ ssm_fused2_kernel(const SsmParams p) {
     for (int it = 0; it < n_my; ++it, pt += nslots) {
       const int tb = it & 1;
       const int tile = 2 * pt + (int)rank;          // tile >= ntiles (odd tile count): every map read falls outside and yields zeros
-      if (lane == 0) mbar_wait_cluster(bar_taps_empty + 8 * tb, (((uint32_t)it >> 1) & 1u) ^ 1u);
+      if (lane == 0) mbar_wait(bar_taps_empty + 8 * tb, (((uint32_t)it >> 1) & 1u) ^ 1u);
       __syncwarp();
       const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
       const int y0 = ty * TILE_H, x0 = tx * TILE_W;
@@ -263,7 +242,7 @@ ssm_fused2_kernel(const SsmParams p) {
         __syncwarp();
         ITG_SACC(1, tl);
         const uint32_t d = tmem_base + (uint32_t)(b * p.n_blk);
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < SSM_GROUPS; ++g) {
           if (lane == 0) mbar_wait(bar_a_full + 8 * g, (uint32_t)it & 1u);
           __syncwarp();
@@ -312,7 +291,7 @@ ssm_fused2_kernel(const SsmParams p) {
         const int my = ty * TILE_H + hy, mx = tx * TILE_W + hx;
         ring = my == 0 || mx == 0 || my >= p.h + 1 || mx >= p.w + 1;
       }
-      if (lane == 0) mbar_wait_cluster(bar_mlp_full, (uint32_t)it & 1u);
+      if (lane == 0) mbar_wait(bar_mlp_full, (uint32_t)it & 1u);
       __syncwarp();
       ITG_SACC(0, tl);
       tc_fence_after();
@@ -321,13 +300,13 @@ ssm_fused2_kernel(const SsmParams p) {
       uint32_t r[32];
       tmem_ld32_issue(trow, r);
       tmem_ld_wait(r);
-#pragma unroll
+#pragma unroll 1
       for (int g = 0; g < SSM_GROUPS; ++g) {
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = ring ? 0u : pack2<T>(fmaxf(__uint_as_float(r[2 * i]), 0.f), fmaxf(__uint_as_float(r[2 * i + 1]), 0.f));
         if (g + 1 < SSM_GROUPS) tmem_ld32_issue(trow + (uint32_t)(32 * (g + 1)), r);
-        if (lane == 0) mbar_wait_cluster(bar_a_empty + 8 * g, ((uint32_t)it & 1u) ^ 1u);
+        if (lane == 0) mbar_wait(bar_a_empty + 8 * g, ((uint32_t)it & 1u) ^ 1u);
         __syncwarp();
         ITG_SACC(1, tl);
         if (hp_ok && !(p.exp & 2)) {
@@ -375,7 +354,7 @@ ssm_fused2_kernel(const SsmParams p) {
           xr[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(ep.mod_x) +
                                                   grid_off(y >> ep.mod_shift, x >> ep.mod_shift, ep.mod_w, ep.mod_c, n >> 1));
       }
-      if (lane == 0) mbar_wait_cluster(bar_acc_full + 8 * b, ((uint32_t)it >> 1) & 1u);
+      if (lane == 0) mbar_wait(bar_acc_full + 8 * b, ((uint32_t)it >> 1) & 1u);
       __syncwarp();
       ITG_SACC(0, tl);
       tc_fence_after();

@@ -34,11 +34,13 @@ PRECISIONS = {
     # name: (torch dtype, conv implementation)
     "fp32": (torch.float32, L.IMPL_DIRECT),     # exact mode: CUDA-core fp32 (the <= 1e-3 gate)
     "fp16": (torch.float16, L.IMPL_AUTO),       # tcgen05 kind::f16, fp16 operands / fp32 accumulate
-    "bf16": (torch.bfloat16, L.IMPL_AUTO),      # tcgen05 kind::f16, bf16 operands / fp32 accumulate
     "fp16-stream": (torch.float16, L.IMPL_UMMA),     # force the per-tap streaming kernel everywhere, SSM as two launches (A/B comparison)
     "fp16-direct": (torch.float16, L.IMPL_DIRECT),   # on-device cross-check of the tcgen05 kernel
-    "bf16-direct": (torch.bfloat16, L.IMPL_DIRECT),
 }
+# There is deliberately no 'bf16' entry.  Single-pass bf16 operands (7 mantissa bits) measure 2.7e-2 ... 6.8e-2 max-abs on the [-1, 1] image at
+# random init (SURVEY 7.4 predicted 4e-2 ... 1e-1), above the <= 2e-2 gate of the 16-bit mode; fp16 operands run on the same tcgen05 kind::f16
+# path at the same rate and meet it (<= 1.9e-2 on every fixture), and the Generator's activations stay below 14, far inside fp16's range.  The
+# kernels keep their bf16 instantiations (launch-level tests compare them with the emulator), but the product does not offer the mode.
 
 SSM_HIDDEN = 128   # nhidden of StochasticSpatialModulation (models/layers.py:220)
 ALIGN = 1024       # arena alignment in bytes (TMA needs 16; keep tensors on separate 1 KiB lines)
@@ -183,7 +185,7 @@ class Plan:
             self.maps_in = [alloc((th * cfg.level_res(k) + 4, tw * cfg.level_res(k) + 4), dtype=torch.float32,
                                   device=device) for k in range(1, cfg.n_layers_G + 1)]
             if cfg.nonlocal_mode and not self.fuse_ssm:
-                raise NotImplementedError("the non-local SSM Generator runs on the fused 16-bit kernel only (precision 'fp16' / 'bf16')")
+                raise NotImplementedError("the non-local SSM Generator runs on the fused 16-bit kernel only (precision 'fp16')")
         if img_layout == L.IMG_MERGED:
             self.out = torch.empty((1, cfg.img_ch, th * P, tw * P), dtype=torch.float32, device=device)
         else:
@@ -559,7 +561,9 @@ class Engine:
     def __init__(self, cfg: GenConfig, state_dict: Dict[str, torch.Tensor], precision: str = "fp16", device="cuda",
                  backend=None):
         if precision not in PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+            hint = (" (single-pass bf16 operands cannot meet the 2e-2 image tolerance; 'fp16' runs on the same tensor-core path at the same rate)"
+                    if precision.startswith("bf16") else "")
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}{hint}")
         if cfg.nonlocal_mode:
             # the non-local Generator is fully convolutional over the whole image: plans address the h x w latent grid as an h x w grid
             # of 1-pixel "patches" (base_res 1) with a zero frame

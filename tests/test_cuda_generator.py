@@ -4,8 +4,8 @@ Ground truth: tests/golden/*.npz = outputs of the UNMODIFIED reference (CPU fp32
 (tests/golden/make_golden.py), plus the CPU oracle for cases generated on the fly.
 
 Tolerances on the [-1, 1] image (BASELINE.json north_star): max-abs <= 1e-3 in fp32 mode, <= 2e-2 in 16-bit
-mode.  fp16 operands meet 2e-2; single-pass bf16 does not at random init (4e-2..1e-1) and is
-held to 1.5e-1 here with the measured value printed -- see DESIGN.md "Numerics".
+mode.  The 16-bit mode is fp16 operands; single-pass bf16 cannot meet 2e-2 at random init (4e-2..1e-1,
+measured 2.7e-2..6.8e-2 in round 1) and is not offered by the product -- see DESIGN.md "Numerics".
 """
 import pytest
 import torch
@@ -15,10 +15,10 @@ from oracle import itg_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-3, "fp16": 2e-2, "bf16": 1.5e-1}
+TOL = {"fp32": 1e-3, "fp16": 2e-2}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
 @pytest.mark.parametrize("name", CASES)
 def test_oneshot_matches_reference(name, precision):
     """One device-resident forward of the whole grid == reference one-shot forward (Oracle A)."""

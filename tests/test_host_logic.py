@@ -267,3 +267,11 @@ def test_nonlocal_limits_are_reported():
         net(torch.zeros(1, kw["z_dim"], 6, 6))                       # attention over a 24x24 map is not served
     with pytest.raises(ValueError, match="padding_mode"):
         itg.ResidualPatchGenerator(**kw, padding_mode="reflect")
+
+
+def test_bf16_mode_is_refused_with_a_reason():
+    """Single-pass bf16 operands miss the 2e-2 image tolerance; the product offers fp16 (same tensor-core rate) and says so."""
+    d, kw, ocfg, sd, z, maps = load_case("gen_bn4_att_rep")
+    net = make_generator(kw, sd, "bf16", backend=EmulatorBackend())
+    with pytest.raises(ValueError, match="cannot meet the 2e-2"):
+        net.engine()
