@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libitg_b200.so")
+LIB_PATH = os.environ.get("ITG_B200_LIB") or os.path.join(_HERE, "libitg_b200.so")     # (override: A/B runs of two builds of the library)
 
 # enums of include/itg.h
 F32, F16, BF16 = 0, 1, 2
