@@ -63,6 +63,8 @@ struct TileParams {
   uint32_t idesc;
   const void* w;
   unsigned long long* dbg;  // optional [grid][16] cycle counters (ITG_TILE_DBG=1), NULL in production
+  int exp;                  // developer experiments (ITG_TILE_EXP bit mask, read with ITG_TILE_DBG only; WRONG RESULTS, timing only):
+                            // 1 producer issues no loads, 2 epilogue does not store, 4 MMA warp issues one tap only
   EpiParams ep;
 };
 
@@ -208,17 +210,37 @@ conv_tile_kernel(const TileParams p) {
     const int s0 = pw * p.ring;            // first stage of this pipeline's private ring
     int s = s0;                            // stage of tile k
     uint32_t ph = 0;
-    int s_pub = s0;                        // stage of the tile to publish (ahead iterations behind)
-    int k = 0;
+    int s_pub = s0;                        // stage of the oldest tile that is loaded (or loading) but not yet published
+    int k = 0, k_pub = 0;                  // tiles issued / published
+    auto publish_upto = [&](int k_end) {   // tiles [k_pub, k_end) have landed: hand them to the MMA warp
+      fence_proxy_async();
+      for (; k_pub < k_end; ++k_pub) {
+        mbar_arrive(bar_full + 8 * s_pub);
+        if (++s_pub == s0 + p.ring) s_pub = s0;
+      }
+    };
     for (; tile < p.ntiles; tile += step, ++k) {
       const int y0 = ty * TILE_H, x0 = tx * TILE_W;                            // halo origin in buffer pixels
-      if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-      __syncwarp();
+      // A free stage for tile k means the MMAs of tile k - ring have finished.  If that is not yet the case, everything loaded so far is
+      // published BEFORE sleeping: with a two-stage ring the old order (publish tile k-1 only after tile k's loads were issued) chained
+      // MMA(k) behind MMA(k-1) plus a whole load-issue pass -- the K = 64 layers ran at a third of their MMA rate with the loads idle.
+      uint32_t ready = 0;
+      if (lane == 0) ready = mbar_try_wait(bar_empty + 8 * s, ph ^ 1u) ? 1u : 0u;
+      ready = __shfl_sync(0xffffffffu, ready, 0);
+      if (!ready) {
+        if (k_pub < k) {
+          cp_async_wait_dyn(0);
+          publish_upto(k);
+        }
+        if (lane == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        __syncwarp();
+      }
       ITG_ACC(0, tl);
       const uint32_t dst0 = a_smem + (uint32_t)(s * p.stage_bytes) + plane_off;
       const T* src0 = in + ((size_t)y0 * p.in_pitch + x0) * (size_t)p.in_c + ch_off;
       const bool inside = cg_ok && (y0 + HALO_H <= p.buf_h) && (x0 + HALO_W <= p.buf_w);
-      if (inside) {
+      if (p.exp & 1) {
+      } else if (inside) {
 #pragma unroll 4
         for (int px = px0; px < HALO_PX; px += px_step) {
           const int hy = (px * 205) >> 11, hx = px - hy * HALO_W;
@@ -233,23 +255,17 @@ conv_tile_kernel(const TileParams p) {
       }
       cp_async_commit();
       ITG_ACC(1, tl);
-      if (k >= p.ahead) {                                // this warp's tile (k - ahead) has landed: publish it to the MMA warp
+      if (k + 1 - k_pub > p.ahead) {                     // keep at most `ahead` tiles in flight: the older ones have landed, publish them
         cp_async_wait_dyn(p.ahead);
         ITG_ACC(2, tl);
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * s_pub);
-        if (++s_pub == s0 + p.ring) s_pub = s0;
+        publish_upto(k + 1 - p.ahead);
         ITG_ACC(3, tl);
       }
       if (++s == s0 + p.ring) { s = s0; ph ^= 1u; }
       tx += sdx; ty += sdy; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
     }
     cp_async_wait_dyn(0);
-    fence_proxy_async();
-    for (int q = (k > p.ahead ? k - p.ahead : 0); q < k; ++q) {
-      mbar_arrive(bar_full + 8 * s_pub);
-      if (++s_pub == s0 + p.ring) s_pub = s0;
-    }
+    publish_upto(k);
     if (p.dbg && pw == 0 && lane == 0) for (int i = 0; i < 4; ++i) p.dbg[blockIdx.x * 16 + i] = dbg_acc[i];
   } else if (warp < TILE_MMA_WARPS) {                                          // ---- MMA warps (uniform; one lane issues), tiles it = mw (mod NM) ----
     const int mw = warp;
@@ -277,7 +293,8 @@ conv_tile_kernel(const TileParams p) {
       const uint32_t a16 = (a_smem + (uint32_t)(s * p.stage_bytes)) >> 4;
       if (elect_one_sync()) {                                                    // one elected lane issues the whole tile from a branch that ptxas
         const uint32_t d0 = tmem_base + (uint32_t)(b * NPHASE * p.n);            // recognises as single-threaded: descriptors stay on the uniform datapath
-        if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        if (p.exp & 4) issue_tile<ITG_CONV1X1, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
+        else if (ksteps == 1) issue_tile<MODE, 1>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
         else if (ksteps == 2) issue_tile<MODE, 2>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
         else issue_tile<MODE, 4>(d0, a16, w16, n16, (uint32_t)p.kg, p.idesc);
         umma_commit(bar_empty + 8 * s);                                        // input stage may be refilled
@@ -316,7 +333,7 @@ conv_tile_kernel(const TileParams p) {
       const int b = it & (p.nbuf - 1);
       const uint32_t bph = (uint32_t)(it >> nbuf_log2) & 1u;
       const int y = ty * TILE_H + (row >> 3), x = tx * TILE_W + (row & 7);
-      const bool valid = (y < p.m_h) && (x < p.m_w);
+      const bool valid = (y < p.m_h) && (x < p.m_w) && !(p.exp & 2);
       // residual rows do not depend on the accumulators: fetch them before sleeping on the MMA barrier (fetching them a
       // whole tile ahead was measured slower: the extra live registers spill under the 80-register cap)
       uint4 pre[8];
@@ -337,7 +354,7 @@ conv_tile_kernel(const TileParams p) {
       ITG_ACC(0, tl);
       tc_fence_after();
       // interior tile: every pixel valid and none of its outputs on the image border (no frame writes needed)
-      const bool interior = fast && ty > 0 && tx > 0 && (ty + 1) * TILE_H < p.m_h && (tx + 1) * TILE_W < p.m_w;
+      const bool interior = fast && ty > 0 && tx > 0 && (ty + 1) * TILE_H < p.m_h && (tx + 1) * TILE_W < p.m_w && !(p.exp & 2);
       if (interior) {
 #pragma unroll
         for (int q = 0; q < NPHASE; ++q) {

@@ -437,6 +437,7 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
     if (!dbg_buf) ITG_CUDA(cudaMalloc(&dbg_buf, (4096 + 128) * sizeof(unsigned long long)));
     ITG_CUDA(cudaMemsetAsync(dbg_buf, 0, (4096 + 128) * sizeof(unsigned long long), st));
     p.dbg = dbg_buf;
+    p.exp = getenv("ITG_TILE_EXP") ? atoi(getenv("ITG_TILE_EXP")) : 0;       // timing experiments (wrong results), debug mode only
   }
   // epilogue specialisations of the Generator's thin layers; anything else takes the run-time generic instance
   int flags = itg::EF_GENERIC;

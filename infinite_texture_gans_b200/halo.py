@@ -39,9 +39,18 @@ class SequentialHalo:
     def __init__(self, backend, nph: int, npw: int, replicate: bool):
         self.be, self.nph, self.npw, self.replicate = backend, nph, npw, replicate
         self.layers: Dict[str, _LayerState] = {}
+        self._pool: Dict[tuple, List[torch.Tensor]] = {}      # retired halo buffers by (shape, dtype, device): steady state allocates nothing
 
     def reset(self) -> None:
         self.layers.clear()
+
+    def _get(self, shape, like: torch.Tensor) -> torch.Tensor:
+        free = self._pool.get((tuple(shape), like.dtype, like.device))
+        return free.pop() if free else torch.empty(shape, dtype=like.dtype, device=like.device)
+
+    def _put(self, t: Optional[torch.Tensor]) -> None:
+        if t is not None:
+            self._pool.setdefault((tuple(t.shape), t.dtype, t.device), []).append(t)
 
     def hooks(self, plan: Plan, loc: str):
         return {hp.step: (lambda hp=hp: self.apply(hp, loc)) for hp in plan.halo_points}
@@ -59,23 +68,25 @@ class SequentialHalo:
 
         # ---- update_padding_variables (models/layers.py:103-143) ----
         if st.col_next is not None:
+            self._put(st.col)
             st.col, st.col_next = st.col_next, None
         if not last_col:
             # column W*(npw-1)-1 of the merged input; frame rows travel along and become the corners
-            nxt = torch.empty((H + 2, 1, C), dtype=buf.dtype, device=buf.device)
+            nxt = self._get((H + 2, 1, C), buf)
             be.copy_rect(buf, 0, w * (self.npw - 1), nxt, 0, 0, H + 2, 1)
             st.col_next = nxt
         ncols = W if last_col else w * (self.npw - 1)
-        part = torch.empty((1, ncols, C), dtype=buf.dtype, device=buf.device)
+        part = self._get((1, ncols, C), buf)
         be.copy_rect(buf, w * (self.nph - 1), 1, part, 0, 0, 1, ncols)      # row H*(nph-1)-1
         if first_col:
             if not first_row:
                 total = sum(p.shape[1] for p in st.row_parts)
-                cur = torch.empty((1, total + 2, C), dtype=buf.dtype, device=buf.device)
+                cur = self._get((1, total + 2, C), buf)
                 x = 1
                 for p in st.row_parts:
                     be.copy_rect(p, 0, 0, cur, 0, x, 1, p.shape[1])
                     x += p.shape[1]
+                    self._put(p)
                 if self.replicate:                                           # F.pad(row, (1,1,0,0), outer_padding)
                     be.copy_rect(cur, 0, 1, cur, 0, 0, 1, 1)
                     be.copy_rect(cur, 0, total, cur, 0, total + 1, 1, 1)
@@ -99,6 +110,7 @@ class SequentialHalo:
             if not first_row:
                 be.copy_rect(st.row_cur, 0, st.row_off, buf, 0, 0, 1, W + 2)
             if last_col:
+                self._put(st.row_cur)
                 st.row_cur = None
             else:
                 st.row_off += (self.npw - 1) * w

@@ -61,6 +61,28 @@ def test_default_sampler_call_reproduces_the_reference_sampler(name):
         itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], base_res=8, output_resolution_height=H, output_resolution_width=W)
 
 
+@pytest.mark.parametrize("nps,H,W", [(4, 224, 320), (5, 288, 416), (3, 150, 200)])
+def test_sequential_schedule_other_subimage_sizes_on_the_device(nps, H, W):
+    """utils.py:258-259 takes num_patches_height / num_patches_width: square sub-images of 3..5 patches, sizes that are not multiples of the
+    patch, attention.gamma != 0 -- the device-resident halo state machine (halo.SequentialHalo, pooled buffers) against Oracle B."""
+    import infinite_texture_gans_b200 as itg
+    kw = dict(z_dim=16, G_ch=8, n_layers_G=4, attention=True, leak=0.02, type_norm="BN", outer_padding="replicate")
+    ocfg = O.GenCfg(**kw, num_patches_h=nps, num_patches_w=nps)
+    sd = O.make_state_dict(ocfg, 5, stress=True)
+    geo = O.geometry(H, W, ocfg)
+    z, _ = O.make_noise(ocfg, geo["total_h"], geo["total_w"], 3)
+    with torch.no_grad():
+        ref = O.sample_patch_by_patch(sd, ocfg, H, W, z)
+    for precision in ("fp32", "fp16"):
+        net = make_generator(kw, sd, precision, "cuda")
+        for _ in range(2):                                   # the second sweep runs entirely on pooled halo buffers
+            got = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=16, num_patches_height=nps, num_patches_width=nps,
+                                                              output_resolution_height=H, output_resolution_width=W,
+                                                              schedule="sequential", noise=(z, None))
+        assert tuple(got.shape) == (1, 3, H, W)
+        assert (got - ref).abs().max().item() <= TOL[precision]
+
+
 def test_forward_signature_and_patch_layout():
     """netG(z, maps, image_location) returns (nph*npw, img_ch, P, P) patches in row-major order (generators.py:86-124)."""
     import infinite_texture_gans_b200 as itg
