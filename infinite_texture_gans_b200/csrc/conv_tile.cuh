@@ -240,6 +240,16 @@ conv_tile_kernel(const TileParams p) {
       const T* src0 = in + ((size_t)y0 * p.in_pitch + x0) * (size_t)p.in_c + ch_off;
       const bool inside = cg_ok && (y0 + HALO_H <= p.buf_h) && (x0 + HALO_W <= p.buf_w);
       if (p.exp & 1) {
+#ifndef ITG_NO_1X1_INTERIOR
+      } else if (MODE == ITG_CONV1X1 && inside) {
+        // a 1x1 conv reads no neighbours: only the 16 x 8 interior of the halo tile is fetched (29 % fewer bytes and copies; the ring keeps
+        // whatever an earlier tile left there and is never addressed by the single tap)
+#pragma unroll 4
+        for (int px = px0; px < TILE_W * TILE_H; px += px_step) {
+          const int hy = (px >> 3) + 1, hx = (px & 7) + 1;
+          cp_async16(dst0 + (uint32_t)((hy * HALO_W + hx) * 16), src0 + (uint32_t)((hy * p.in_pitch + hx) * p.in_c));
+        }
+#endif
       } else if (inside) {
 #pragma unroll 4
         for (int px = px0; px < HALO_PX; px += px_step) {
