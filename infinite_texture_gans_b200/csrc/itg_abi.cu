@@ -16,6 +16,7 @@
 #include "conv_tile.cuh"
 #include "ssm_fused.cuh"
 #include "ssm_fused2.cuh"
+#include "conv_pair.cuh"
 
 namespace {
 
@@ -495,6 +496,96 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
+// 3x3 layers with 32 <= k_pad <= 128 on CTA pairs (conv_pair.cuh): activations read once per tile, weights resident
+bool pair_eligible(const itg_conv_desc& d) {
+  if (d.dtype == ITG_F32 || d.mode != ITG_CONV3X3) return false;
+  if (d.k_pad != 32 && d.k_pad != 64 && d.k_pad != 128) return false;
+  if (d.out_img || d.out_f32 || d.mod_x || d.res_kind == ITG_RES_F32) return false;      // final conv / SSM embed / fp32 residual: other kernels
+  const int nblocks = (d.n_pad + itg::SSM2_NPAIR_MAX - 1) / itg::SSM2_NPAIR_MAX;
+  return nblocks <= 2 && sm_count() >= 4;
+}
+// ... and where they are the better choice (AUTO): enough tiles to fill every pair several times over
+bool pair_preferred(const itg_conv_desc& d) {
+  static const int mode = getenv("ITG_CONV_PAIR") ? atoi(getenv("ITG_CONV_PAIR")) : 1;      // 0 never, 1 default rule, 2 whenever eligible
+  if (mode == 0 || !pair_eligible(d)) return false;
+  if (mode == 2) return true;
+  const int ntiles = ((d.in_w + itg::TILE_W - 1) / itg::TILE_W) * ((d.in_h + itg::TILE_H - 1) / itg::TILE_H);
+  return d.k_pad == 128 && ntiles >= 8 * sm_count();      // K <= 64: the thin-layer kernel is as fast or faster (profiles/r02_notes.md, note 10)
+}
+
+template <typename T>
+int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
+  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 conv with 16-bit operands, k_pad in {32, 64, 128}, n_pad <= 256 and grid outputs");
+  itg::PairParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_h = d.in_h; p.m_w = d.in_w;
+  p.tiles_x = (d.in_w + itg::TILE_W - 1) / itg::TILE_W;
+  p.ntiles = p.tiles_x * ((d.in_h + itg::TILE_H - 1) / itg::TILE_H);
+  p.in = d.in; p.in_c = d.in_c; p.in_pitch = d.in_pitch ? d.in_pitch : d.in_w + 2;
+  p.buf_h = d.in_h + 2; p.buf_w = d.in_w + 2;
+  p.in_cg_off = d.in_c_off / 8;
+  p.kg = d.k_pad / 8;
+  const int k_real = d.k < d.k_pad ? d.k : d.k_pad;
+  p.ksteps = (k_real + 15) / 16;
+  p.w = d.w; p.n_pad = d.n_pad; p.k_pad = d.k_pad;
+  p.nblocks = (d.n_pad + itg::SSM2_NPAIR_MAX - 1) / itg::SSM2_NPAIR_MAX;
+  p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 15) / 16 * 16;
+  p.nbuf = p.n_blk <= 64 ? 4 : 2;
+  const int nring = itg::PAIR_A_PLANES / (p.kg < 8 ? p.kg : 8);
+  static const int env_inflight = getenv("ITG_PAIR_INFLIGHT") ? atoi(getenv("ITG_PAIR_INFLIGHT")) : 0;      // developer sweeps
+  p.inflight = env_inflight < 1 || env_inflight > nring - 1 ? nring - 1 : env_inflight;
+  const int sms = sm_count();
+  int nslots = (sms / 2) / p.nblocks;
+  const int npt = (p.ntiles + 1) / 2;
+  if (nslots > npt) nslots = npt;
+  const int grid = 2 * nslots * p.nblocks;
+  const uint32_t fmt = (d.dtype == ITG_BF16) ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_blk >> 3) << 17) | ((256u >> 4) << 24);
+  p.ep = make_epi(d);
+  const int flags = (d.res_kind == ITG_RES_GRID ? itg::EF_RES : 0) | (d.out_raw ? itg::EF_RAW : 0) | (d.out_act ? itg::EF_ACT : 0);
+  const int smem = itg::PAIR_SMEM;
+  static const bool dbg_on = getenv("ITG_TILE_DBG") != nullptr;      // developer aid (counters need a -DITG_SSM_DBG build), synchronous
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) ITG_CUDA(cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long)));
+    ITG_CUDA(cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), st));
+    p.dbg = dbg_buf;
+    p.exp = getenv("ITG_TILE_EXP") ? atoi(getenv("ITG_TILE_EXP")) : 0;       // timing experiments (wrong results), debug mode only
+  }
+#define ITG_PAIR_LAUNCH(FL)                                                                                           \
+  do {                                                                                                                \
+    static bool attr_set[MAX_DEVICES] = {false};                                                                      \
+    const int dev_ = current_device();                                                                                \
+    if (!attr_set[dev_]) {                                                                                            \
+      ITG_CUDA(cudaFuncSetAttribute(itg::conv_pair_kernel<T, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set[dev_] = true;                                                                                          \
+    }                                                                                                                 \
+    ITG_CUDA(launch_pdl_cluster(itg::conv_pair_kernel<T, FL>, dim3(grid), dim3(itg::SSM_THREADS), smem, st, 2, p));    \
+  } while (0)
+  constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
+  switch (flags) {
+    case A: ITG_PAIR_LAUNCH(A); break;
+    case R: ITG_PAIR_LAUNCH(R); break;
+    case A | S: ITG_PAIR_LAUNCH(A | S); break;
+    case R | A: ITG_PAIR_LAUNCH(R | A); break;
+    case R | S: ITG_PAIR_LAUNCH(R | S); break;
+    case R | A | S: ITG_PAIR_LAUNCH(R | A | S); break;
+    default: ITG_PAIR_LAUNCH(G); break;
+  }
+#undef ITG_PAIR_LAUNCH
+  if (dbg_on) {
+    unsigned long long hst[16];
+    ITG_CUDA(cudaStreamSynchronize(st));
+    ITG_CUDA(cudaMemcpy(hst, dbg_buf, sizeof(hst), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[itg pair dbg] %dx%d k_pad=%d ksteps=%d n_pad=%d n_blk=%d nblocks=%d tiles=%d grid=%d nbuf=%d inflight=%d flags=%d | kcycles CTA0: mma.wait_acc=%.1f mma.wait_a=%.1f "
+            "mma.issue=%.1f ld.wait_empty=%.1f ld.issue=%.1f ld.wait_group+publish=%.1f epi.wait=%.1f epi.work=%.1f\n",
+            d.in_h, d.in_w, d.k_pad, p.ksteps, d.n_pad, p.n_blk, p.nblocks, p.ntiles, grid, p.nbuf, p.inflight, flags, hst[0] / 1e3, hst[1] / 1e3, hst[2] / 1e3,
+            hst[4] / 1e3, hst[5] / 1e3, hst[6] / 1e3, hst[8] / 1e3, hst[9] / 1e3);
+  }
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
 // StochasticSpatialModulation as one launch: CTA pairs with tcgen05.mma.cta_group::2 (ssm_fused2.cuh), or single CTAs (ssm_fused.cuh;
 // ITG_SSM_CG=1, and whenever the pair kernel cannot serve the shape)
 template <typename T>
@@ -604,7 +695,13 @@ int itg_conv_fwd(const itg_conv_desc* desc, void* stream) {
   if (rc != ITG_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int impl = d.impl;
-  if (impl == ITG_IMPL_AUTO) impl = (d.dtype == ITG_F32) ? ITG_IMPL_DIRECT : (tile_eligible(d) ? ITG_IMPL_TILE : ITG_IMPL_UMMA);
+  if (impl == ITG_IMPL_AUTO)
+    impl = (d.dtype == ITG_F32) ? ITG_IMPL_DIRECT : (pair_preferred(d) ? ITG_IMPL_PAIR : (tile_eligible(d) ? ITG_IMPL_TILE : ITG_IMPL_UMMA));
+  if (impl == ITG_IMPL_PAIR) {
+    if (d.dtype == ITG_F16) return launch_pair<__half>(d, st);
+    if (d.dtype == ITG_BF16) return launch_pair<__nv_bfloat16>(d, st);
+    return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair path needs 16-bit operands");
+  }
   if (impl == ITG_IMPL_TILE) {
     if (d.dtype == ITG_F16) return launch_tile<__half>(d, st);
     if (d.dtype == ITG_BF16) return launch_tile<__nv_bfloat16>(d, st);

@@ -13,7 +13,7 @@ import torch
 from emulator import EmulatorBackend
 from infinite_texture_gans_b200 import _lib as L
 from infinite_texture_gans_b200 import packing as PK
-from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid, SsmOp, c_store
+from infinite_texture_gans_b200.ops import AttentionOp, ConvOp, Grid, SsmOp, c_store, k_pad_of
 
 pytestmark = pytest.mark.gpu
 
@@ -88,6 +88,13 @@ CONV_CASES = [
     ("up", 40, 56, 64, 48, dict(act=True, border=L.BORDER_REPLICATE)),
     ("3x3", 90, 70, 32, 32, dict(raw=True, act=True, res=0, border=L.BORDER_REPLICATE)),
     ("3x3", 50, 38, 32, 32, dict(raw=True, res=1, border=L.BORDER_NONE)),
+    # CTA-pair kernel: odd tile counts (the last pair's second CTA idles), K = 104 of 128 (seven of eight k-steps), two column blocks,
+    # every ring depth (K = 32 / 64 / 128: four / two / one tile in flight)
+    ("3x3", 136, 120, 104, 52, dict(raw=True, border=L.BORDER_NONE)),
+    ("3x3", 72, 56, 104, 104, dict(raw=True, act=True, res=1, border=L.BORDER_REPLICATE)),
+    ("3x3", 40, 24, 128, 208, dict(act=True, res=0, border=L.BORDER_CONSTANT)),
+    ("3x3", 150, 90, 52, 26, dict(raw=True, border=L.BORDER_NONE)),
+    ("3x3", 9, 7, 26, 26, dict(raw=True, res=0, border=L.BORDER_NONE)),
 ]
 
 
@@ -158,14 +165,17 @@ def _check_conv(opc: ConvOp, opg: ConvOp, dtype):
 
 
 @pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA),
-                                            ("bf16", L.IMPL_UMMA), ("fp16", L.IMPL_TILE), ("bf16", L.IMPL_TILE)],
-                         ids=["fp32-direct", "fp16-direct", "fp16-umma", "bf16-umma", "fp16-tile", "bf16-tile"])
+                                            ("bf16", L.IMPL_UMMA), ("fp16", L.IMPL_TILE), ("bf16", L.IMPL_TILE),
+                                            ("fp16", L.IMPL_PAIR), ("bf16", L.IMPL_PAIR)],
+                         ids=["fp32-direct", "fp16-direct", "fp16-umma", "bf16-umma", "fp16-tile", "bf16-tile", "fp16-pair", "bf16-pair"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}")
 def test_conv_matches_emulator(be, case, precision, impl):
     mode, H, W, cin, cout, ex = case
     dtype = DT[precision]
     if impl == L.IMPL_TILE and (cin > 64 or cout > 64):
         pytest.skip("halo-tile kernel serves k_pad <= 64, n_pad <= 64")
+    if impl == L.IMPL_PAIR and (mode != "3x3" or "img" in ex or k_pad_of(c_store(cin)) not in (32, 64, 128) or cout > 256):
+        pytest.skip("CTA-pair kernel serves 3x3 grid-to-grid convs with k_pad 32 | 64 | 128")
     opc = _make_conv(mode, H, W, cin, cout, ex, dtype, impl, seed=H * 1000 + W * 10 + cin + cout)
     opg = _run_both(be, opc, _conv_to_dev)
     _check_conv(opc, opg, dtype)

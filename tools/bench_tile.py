@@ -32,6 +32,10 @@ def run(name, mode, H, W, cin, cout, res=None, reps=5):
     taps = 9 if mode == L.CONV3X3 else 1
     print(f"{name:28s} exp={os.environ.get('ITG_TILE_EXP','0')} {ms:7.3f} ms  {2 * taps * cin * cout * H * W / ms / 1e9:7.1f} TFLOP/s", flush=True)
 S = 3904
+if os.environ.get("BENCH_TILE_ALL"):
+    run("block3.conv2 3x3 104->104+res", L.CONV3X3, S // 4, S // 4, 104, 104, res=0)
+    run("block4.conv1 3x3 104->52", L.CONV3X3, S // 2, S // 2, 104, 52)
+    run("block4.conv2 3x3 52->52+res", L.CONV3X3, S // 2, S // 2, 52, 52, res=0)
 run("block5.conv1 3x3 52->26", L.CONV3X3, S, S, 52, 26)
 run("block5.conv3 1x1 52->26", L.CONV1X1, S, S, 52, 26)
 run("block5.conv2 3x3 26->26+res", L.CONV3X3, S, S, 26, 26, res=0)

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
+for v in "ITG_PAIR_INFLIGHT=1" "ITG_PAIR_INFLIGHT=2" "ITG_PAIR_INFLIGHT=4"; do
+  echo "== $v"; env $v ITG_CONV_PAIR=2 ITG_TILE_DBG=1 ITG_B200_LIB=$PWD/build_variants/libitg_dbg.so BENCH_TILE_ALL=1 timeout 100 python tools/bench_tile.py 2>&1 | grep -E "pair dbg" | awk 'NR%7==1' | cut -c1-400
+done
