@@ -496,13 +496,13 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
-// 3x3 layers with 32 <= k_pad <= 128 on CTA pairs (conv_pair.cuh): activations read once per tile, weights resident
+// 3x3 layers with k_pad <= 128 on CTA pairs (conv_pair.cuh): activations read once per tile, weights resident
 bool pair_eligible(const itg_conv_desc& d) {
   if (d.dtype == ITG_F32 || d.mode != ITG_CONV3X3) return false;
-  if (d.k_pad != 32 && d.k_pad != 64 && d.k_pad != 128) return false;
+  if (d.k_pad > 128) return false;
   if (d.out_img || d.out_f32 || d.mod_x || d.res_kind == ITG_RES_F32) return false;      // final conv / SSM embed / fp32 residual: other kernels
-  const int nblocks = (d.n_pad + itg::SSM2_NPAIR_MAX - 1) / itg::SSM2_NPAIR_MAX;
-  return nblocks <= 2 && sm_count() >= 4;
+  const int nblocks = (d.n_pad + itg::PAIR_NBLK_MAX - 1) / itg::PAIR_NBLK_MAX;
+  return nblocks <= 4 && sm_count() >= 2 * nblocks;
 }
 // ... and where they are the better choice (AUTO): enough tiles to fill every pair several times over
 bool pair_preferred(const itg_conv_desc& d) {
@@ -510,12 +510,13 @@ bool pair_preferred(const itg_conv_desc& d) {
   if (mode == 0 || !pair_eligible(d)) return false;
   if (mode == 2) return true;
   const int ntiles = ((d.in_w + itg::TILE_W - 1) / itg::TILE_W) * ((d.in_h + itg::TILE_H - 1) / itg::TILE_H);
-  return d.k_pad == 128 && ntiles >= 8 * sm_count();      // K <= 64: the thin-layer kernel is as fast or faster (profiles/r02_notes.md, note 10)
+  static const int min_tiles = getenv("ITG_PAIR_MIN_TILES") ? atoi(getenv("ITG_PAIR_MIN_TILES")) : 8 * sm_count();
+  return d.k_pad >= 64 && ntiles >= min_tiles;      // K = 32: the thin-layer kernel is faster (profiles/r02_notes.md, note 10)
 }
 
 template <typename T>
 int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
-  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 conv with 16-bit operands, k_pad in {32, 64, 128}, n_pad <= 256 and grid outputs");
+  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 conv with 16-bit operands, k_pad <= 128, n_pad <= 256 and grid outputs");
   itg::PairParams p;
   memset(&p, 0, sizeof(p));
   p.m_h = d.in_h; p.m_w = d.in_w;
@@ -524,16 +525,17 @@ int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
   p.in = d.in; p.in_c = d.in_c; p.in_pitch = d.in_pitch ? d.in_pitch : d.in_w + 2;
   p.buf_h = d.in_h + 2; p.buf_w = d.in_w + 2;
   p.in_cg_off = d.in_c_off / 8;
-  p.kg = d.k_pad / 8;
-  const int k_real = d.k < d.k_pad ? d.k : d.k_pad;
-  p.ksteps = (k_real + 15) / 16;
+  p.np = d.k / 8;                                   // validate(): k % 8 == 0, k <= k_pad
+  p.ksteps = (p.np + 1) / 2;
+  p.slot_planes = 2 * p.ksteps;
+  p.nring = itg::PAIR_A_PLANES / p.slot_planes;
+  if (p.nring > itg::PAIR_MAX_SLOTS) p.nring = itg::PAIR_MAX_SLOTS;
   p.w = d.w; p.n_pad = d.n_pad; p.k_pad = d.k_pad;
-  p.nblocks = (d.n_pad + itg::SSM2_NPAIR_MAX - 1) / itg::SSM2_NPAIR_MAX;
+  p.nblocks = (d.n_pad + itg::PAIR_NBLK_MAX - 1) / itg::PAIR_NBLK_MAX;
   p.n_blk = ((d.n_pad + p.nblocks - 1) / p.nblocks + 15) / 16 * 16;
-  p.nbuf = p.n_blk <= 64 ? 4 : 2;
-  const int nring = itg::PAIR_A_PLANES / (p.kg < 8 ? p.kg : 8);
+  p.nbuf = 4;
   static const int env_inflight = getenv("ITG_PAIR_INFLIGHT") ? atoi(getenv("ITG_PAIR_INFLIGHT")) : 0;      // developer sweeps
-  p.inflight = env_inflight < 1 || env_inflight > nring - 1 ? nring - 1 : env_inflight;
+  p.inflight = env_inflight < 1 || env_inflight > p.nring - 1 ? p.nring - 1 : env_inflight;
   const int sms = sm_count();
   int nslots = (sms / 2) / p.nblocks;
   const int npt = (p.ntiles + 1) / 2;
@@ -577,9 +579,9 @@ int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
     unsigned long long hst[16];
     ITG_CUDA(cudaStreamSynchronize(st));
     ITG_CUDA(cudaMemcpy(hst, dbg_buf, sizeof(hst), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[itg pair dbg] %dx%d k_pad=%d ksteps=%d n_pad=%d n_blk=%d nblocks=%d tiles=%d grid=%d nbuf=%d inflight=%d flags=%d | kcycles CTA0: mma.wait_acc=%.1f mma.wait_a=%.1f "
+    fprintf(stderr, "[itg pair dbg] %dx%d k=%d ksteps=%d n_pad=%d n_blk=%d nblocks=%d tiles=%d grid=%d ring=%d inflight=%d flags=%d | kcycles CTA0: mma.wait_acc=%.1f mma.wait_a=%.1f "
             "mma.issue=%.1f ld.wait_empty=%.1f ld.issue=%.1f ld.wait_group+publish=%.1f epi.wait=%.1f epi.work=%.1f\n",
-            d.in_h, d.in_w, d.k_pad, p.ksteps, d.n_pad, p.n_blk, p.nblocks, p.ntiles, grid, p.nbuf, p.inflight, flags, hst[0] / 1e3, hst[1] / 1e3, hst[2] / 1e3,
+            d.in_h, d.in_w, d.k, p.ksteps, d.n_pad, p.n_blk, p.nblocks, p.ntiles, grid, p.nring, p.inflight, flags, hst[0] / 1e3, hst[1] / 1e3, hst[2] / 1e3,
             hst[4] / 1e3, hst[5] / 1e3, hst[6] / 1e3, hst[8] / 1e3, hst[9] / 1e3);
   }
   ITG_CUDA(cudaGetLastError());
