@@ -21,7 +21,8 @@
 //     cluster-multicast, loaders / epilogue warps of both CTAs arrive on the leader's mbarriers;
 //   * eight epilogue warps per CTA drain a ring of four TMEM accumulators (bias, residual, BN + activation, raw / activated outputs,
 //     frame -- the semantics of epilogue8, itg_common.cuh) with coalesced global accesses: a lane owns a pixel, but residual loads and
-//     output stores go through a per-warp transposition buffer so that one instruction covers 8 consecutive pixels x 64 bytes.
+//     output stores go through a per-warp transposition buffer so that one instruction covers 8 consecutive pixels x 64 bytes.  The two
+//     warps of a TMEM lane quarter split the columns of a tile, or alternate tiles when the pair has <= 32 columns.
 #pragma once
 #include "ssm_fused2.cuh"
 
@@ -30,7 +31,7 @@ namespace itg {
 constexpr int PAIR_KG_MAX = 16;                                        // 8-channel planes per tile (K <= 128)
 constexpr int PAIR_NH = 32;                                            // weight rows parked per CTA (row pitch of the weight image)
 constexpr int PAIR_NBLK_MAX = 2 * PAIR_NH;                             // GEMM columns per CTA pair
-constexpr int PAIR_PLANE = PLANE_BYTES + 16;                           // plane pitch 2896 B = 16 (mod 128)
+constexpr int PAIR_PLANE = PLANE_BYTES + 16;                           // plane pitch 2896 B = 16 (mod 128), see TILE_PLANE
 constexpr int PAIR_A_PLANES = 48;                                      // activation ring: 3 x 16 | 6 x 8 | 8 x 4 planes
 constexpr int PAIR_MAX_SLOTS = 8;
 constexpr int PAIR_HDR = 1024;                                         // barriers | at 256: bias, scale, shift of the pair's 64 columns (fp32)
@@ -76,6 +77,7 @@ conv_pair_kernel(const PairParams p) {
   const uint32_t rank = cluster_ctarank();                              // 0 = leader
   const int n_half = p.n_blk >> 1;
   const uint32_t nring = (uint32_t)p.nring;
+  const bool split_tiles = p.n_blk <= 32;            // epilogue: the two warps of a TMEM lane quarter alternate tiles (else they split the columns)
   const uint32_t slot_bytes = (uint32_t)(p.slot_planes * PAIR_PLANE);
 
   const uint32_t bar_a_full = sbase;               // [8]  loaders of both CTAs -> leader's MMA warp        (count 12)
@@ -99,7 +101,7 @@ conv_pair_kernel(const PairParams p) {
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 16);
+      mbar_init(bar_acc_empty + 8 * i, split_tiles ? 8 : 16);
     }
     fence_barrier_init();
   }
@@ -270,9 +272,13 @@ conv_pair_kernel(const PairParams p) {
     const bool has_raw = G ? (ep.out_raw != nullptr) : ((F & EF_RAW) != 0);
     const bool has_act = G ? (ep.out_act != nullptr) : ((F & EF_ACT) != 0);
     const int eg = warp >> 2, q = warp & 3;
-    const int c_lo = eg * n_half;                                       // first column of this warp, relative to n0
+    // <= 32 columns per pair: a warp takes every other tile with all columns (one tile's epilogue is a chain of TMEM / shared / global
+    // latencies longer than the tile's 18-36 MMAs); otherwise both warps work on every tile, half of the columns each
+    const int c_lo = split_tiles ? 0 : eg * n_half;                     // first column of this warp, relative to n0
+    const int ncols = split_tiles ? p.n_blk : n_half;
     int nch = (ep.out_c - (n0 + c_lo) + 7) >> 3;                        // 8-channel chunks this warp stores (columns beyond out_c are padding)
-    nch = nch < 0 ? 0 : (nch > (n_half >> 3) ? (n_half >> 3) : nch);
+    nch = nch < 0 ? 0 : (nch > (ncols >> 3) ? (ncols >> 3) : nch);
+    const int it0 = split_tiles ? eg : 0, it_step = split_tiles ? 2 : 1;
     const uint32_t stage = sbase + PAIR_OFF_STAGE + (uint32_t)warp * 2048u;
     const uint32_t vec = sbase + PAIR_OFF_VEC + (uint32_t)c_lo * 4u;
     // unit r of this lane in memory order: pixel pl = (lane + 32 r) / nch of the warp's 32, chunk k = (lane + 32 r) % nch
@@ -303,9 +309,9 @@ conv_pair_kernel(const PairParams p) {
         }
       }
     };
-    if (has_res && n_my > 0) load_res(slot);
-    int pt = slot;
-    for (int it = 0; it < n_my; ++it, pt += nslots) {
+    if (has_res && it0 < n_my) load_res(slot + it0 * nslots);
+    int pt = slot + it0 * nslots;
+    for (int it = it0; it < n_my; it += it_step, pt += it_step * nslots) {
       const int b = it & (p.nbuf - 1);
       const int tile = 2 * pt + (int)rank;
       const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
@@ -324,7 +330,7 @@ conv_pair_kernel(const PairParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (k < nch) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[k].x), "=r"(pre[k].y), "=r"(pre[k].z), "=r"(pre[k].w) : "r"(my_row + (uint32_t)((k ^ my_swz) << 4)));
-        if (it + 1 < n_my) load_res(pt + nslots);
+        if (it + it_step < n_my) load_res(pt + it_step * nslots);
       }
       if (lane == 0) mbar_wait(bar_acc_full + 8 * b, ((uint32_t)it / (uint32_t)p.nbuf) & 1u);
       __syncwarp();

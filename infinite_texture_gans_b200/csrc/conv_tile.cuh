@@ -27,6 +27,12 @@ constexpr int TILE_W = 8, TILE_H = 16;                       // output tile = 12
 constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;      // input neighbourhood
 constexpr int HALO_PX = HALO_W * HALO_H;                     // 180
 constexpr int PLANE_BYTES = HALO_PX * 16;                    // one 8-channel plane of the halo tile: 2880 B
+#ifndef ITG_TILE_PLANE_PAD
+#define ITG_TILE_PLANE_PAD 16
+#endif
+constexpr int TILE_PLANE = PLANE_BYTES + ITG_TILE_PLANE_PAD;  // plane pitch of the cp.async-filled tiles: 2896 B = 16 (mod 128), so that the kg lanes that copy
+                                                             // the 16-byte chunks of one pixel to kg planes hit different bank groups (tools/ldgsts_probe.cu:
+                                                             // 9 vs 17 cycles per warp instruction)
 // Warp roles: the CTA runs TILE_PIPES independent pipelines.  Pipeline m = producer warp (4 + 4 * PIPES + m), MMA warp m
 // (one per scheduler) and epilogue group m (warps 4 + 4m .. 7 + 4m; TMEM lane quarter = warp % 4); it owns the tiles
 // it = m (mod pipes) of this CTA, a private ring of input stages and private TMEM accumulator buffers.  Every mbarrier
@@ -121,7 +127,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t a16, uint32_t w
       const uint32_t shift16 = (uint32_t)((1 + dy) * HALO_W + (1 + dx));
 #pragma unroll
       for (int ks = 0; ks < KSTEPS; ++ks) {
-        const uint64_t adesc = desc_noswz(a16 + (uint32_t)(2 * ks) * (PLANE_BYTES / 16) + shift16, PLANE_BYTES / 16, HALO_W);
+        const uint64_t adesc = desc_noswz(a16 + (uint32_t)(2 * ks) * (TILE_PLANE / 16) + shift16, TILE_PLANE / 16, HALO_W);
         const uint64_t bdesc = desc_noswz(w16 + ((uint32_t)wt * kg + (uint32_t)(2 * ks)) * n16, n16, 8);
         umma_f16(d0 + (uint32_t)q * n16, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
       }
@@ -199,7 +205,7 @@ conv_tile_kernel(const TileParams p) {
     const int j = lane & (p.kg - 1), px0 = lane >> kg_log2, px_step = 32 >> kg_log2;
     const bool cg_ok = (p.in_cg_off + j) < cg_total;
     const uint32_t ch_off = (uint32_t)((p.in_cg_off + j) * 8);
-    const uint32_t plane_off = (uint32_t)(j * PLANE_BYTES);
+    const uint32_t plane_off = (uint32_t)(j * TILE_PLANE);
     // per-lane offsets of its halo pixels (<= 45 at kg = 2 ... 12 at kg = 8): computed on the fly, two multiplies each
     unsigned long long dbg_acc[4] = {0, 0, 0, 0};
     long long tl = p.dbg ? clock64() : 0;

@@ -387,7 +387,7 @@ bool tile_eligible(const itg_conv_desc& d) {
   if (d.dtype == ITG_F32 || d.k_pad > 64 || d.n_pad > 64) return false;
   const int taps_w = d.mode == ITG_CONV3X3 ? 9 : (d.mode == ITG_CONV1X1 ? 1 : 16);
   const int w_bytes = (taps_w * (d.k_pad / 8) * d.n_pad * 16 + 127) & ~127;
-  const int stage = (d.k_pad / 8) * itg::PLANE_BYTES;
+  const int stage = (d.k_pad / 8) * itg::TILE_PLANE;
   return itg::TILE_HDR_BYTES + 128 + w_bytes + 4 * stage <= TILE_SMEM_BUDGET;
 }
 
@@ -406,7 +406,7 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   p.n = d.n_pad; p.n_src = d.n_pad; p.k_src = d.k_pad;
   p.taps_w = d.mode == ITG_CONV3X3 ? 9 : (d.mode == ITG_CONV1X1 ? 1 : 16);
   p.w_bytes = (p.taps_w * p.kg * p.n * 16 + 127) & ~127;
-  p.stage_bytes = p.kg * itg::PLANE_BYTES;
+  p.stage_bytes = p.kg * itg::TILE_PLANE;
   int stages = (TILE_SMEM_BUDGET - itg::TILE_HDR_BYTES - 128 - p.w_bytes) / p.stage_bytes;
   if (stages > itg::TILE_MAX_STAGES) stages = itg::TILE_MAX_STAGES;
   const int nphase = d.mode == ITG_UPCONV ? 4 : 1;

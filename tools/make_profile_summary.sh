@@ -18,7 +18,7 @@ for line in sys.stdin:
     m = re.search(r"Function : (\S+)", line)
     if m:
         n = m.group(1)
-        fam = next((k for k in ("ssm_fused2", "ssm_fused", "conv_tile", "conv_umma", "attention_mma", "conv_direct", "attention_kernel", "halo_xchg", "noise_normal", "image_to_u8") if k in n), "other")
+        fam = next((k for k in ("ssm_fused2", "ssm_fused", "conv_pair", "conv_tile", "conv_umma", "attention_mma", "conv_direct", "attention_kernel", "halo_xchg", "noise_normal", "image_to_u8") if k in n), "other")
         counts[fam]["kernels"] += 1
         continue
     if fam is None: continue
@@ -40,7 +40,7 @@ echo "## ncu launch list: share of each kernel (cold-cache, serialised; compare 
 echo
 python tools/ncu_summary.py launches gpurun_out/${R}_launches_cfg3.csv
 echo
-echo "(\`ssm_fused2_kernel\`: StochasticSpatialModulation on CTA pairs, \`tcgen05.mma.cta_group::2\`; \`conv_tile_kernel<T, F, MODE>\`: F = epilogue flags RES=1 RAW=2 ACT=4 IMG=8; MODE 0 = 3x3, 1 = 1x1, 2 = folded up-sampling conv; \`conv_umma_kernel<T, F>\` likewise. The FillFunctor launch is bench.py's 256 MiB L2 flush.)"
+echo "(\`ssm_fused2_kernel\`: StochasticSpatialModulation on CTA pairs, \`tcgen05.mma.cta_group::2\`; \`conv_pair_kernel<T, F>\`: 3x3 convs with 64 <= k_pad <= 128 on CTA pairs; \`conv_tile_kernel<T, F, MODE>\`: F = epilogue flags RES=1 RAW=2 ACT=4 IMG=8; MODE 0 = 3x3, 1 = 1x1, 2 = folded up-sampling conv; \`conv_umma_kernel<T, F>\` likewise. The FillFunctor launch is bench.py's 256 MiB L2 flush.)"
 echo
 echo "## CUDA-event time per launch of one step (bench.py, eager launches, L2 warm)"
 echo
