@@ -504,14 +504,17 @@ bool pair_eligible(const itg_conv_desc& d) {
   const int nblocks = (d.n_pad + itg::PAIR_NBLK_MAX - 1) / itg::PAIR_NBLK_MAX;
   return nblocks <= 4 && sm_count() >= 2 * nblocks;
 }
-// ... and where they are the better choice (AUTO): enough tiles to fill every pair several times over
+// ... and where they are the better choice (AUTO)
 bool pair_preferred(const itg_conv_desc& d) {
   static const int mode = getenv("ITG_CONV_PAIR") ? atoi(getenv("ITG_CONV_PAIR")) : 1;      // 0 never, 1 default rule, 2 whenever eligible
   if (mode == 0 || !pair_eligible(d)) return false;
   if (mode == 2) return true;
   const int ntiles = ((d.in_w + itg::TILE_W - 1) / itg::TILE_W) * ((d.in_h + itg::TILE_H - 1) / itg::TILE_H);
-  static const int min_tiles = getenv("ITG_PAIR_MIN_TILES") ? atoi(getenv("ITG_PAIR_MIN_TILES")) : 8 * sm_count();
-  return d.k_pad >= 64 && ntiles >= min_tiles;      // K = 32: the thin-layer kernel is faster (profiles/r02_notes.md, note 10)
+  // The choice must not depend on the grid size: a row band and the whole texture have to run the same kernel for the same layer, or the
+  // band split is no longer bit-identical to the single-GPU result (different kernels accumulate in different orders).  Measured with
+  // min_tiles = 0 against 8 tiles per SM: cfg2 0.598 vs 0.604 ms, cfg5band 5.300 vs 5.303 ms, cfg3 equal.
+  static const int min_tiles = getenv("ITG_PAIR_MIN_TILES") ? atoi(getenv("ITG_PAIR_MIN_TILES")) : 0;      // developer sweeps
+  return d.k_pad >= 64 && ntiles >= min_tiles;      // K <= 32: the thin-layer kernel is faster (profiles/r02_notes.md, note 12)
 }
 
 template <typename T>

@@ -181,6 +181,32 @@ def test_conv_matches_emulator(be, case, precision, impl):
     _check_conv(opc, opg, dtype)
 
 
+@pytest.mark.parametrize("cin,cout", [(104, 52), (52, 26), (26, 26), (208, 104), (13, 13)])
+def test_auto_kernel_choice_does_not_depend_on_the_grid_size(be, cin, cout):
+    """A row band and the whole texture must run the same kernel for the same layer: the same pixels computed as part of a large grid and
+    of a small window around them are bit-identical (two kernels would accumulate in two orders)."""
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    kin, kout = c_store(cin), c_store(cout)
+    H, W, wy, wx, wh, ww = 384, 400, 160, 200, 24, 40            # 1 200 tiles of 16 x 8 against 15
+    big = _grid(H, W, kin, torch.float16, g)
+    big.buf[..., cin:] = 0
+    w = PK.pack_conv3x3(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin), torch.float16).cuda()
+    bias = PK.pad_vec(0.1 * torch.randn(cout, generator=g), w.shape[1]).cuda()
+
+    def run(src_buf, h, wd):
+        src = Grid(src_buf.contiguous().clone().cuda(), h, wd, kin)
+        op = ConvOp(mode=L.CONV3X3, src=src, w=w, k=kin, bias=bias, impl=L.IMPL_AUTO, name="size")
+        op.out_h, op.out_w, op.out_c = h, wd, kout
+        op.out_raw = Grid(torch.zeros(h + 2, wd + 2, kout, dtype=torch.float16, device="cuda"), h, wd, kout)
+        be.conv(op)
+        torch.cuda.synchronize()
+        return op.out_raw.interior.cpu()
+
+    full = run(big.buf, H, W)
+    win = run(big.buf[wy:wy + wh + 2, wx:wx + ww + 2], wh, ww)       # framed window: its frame = the neighbours in the large grid
+    assert torch.equal(win, full[wy:wy + wh, wx:wx + ww])
+
+
 @pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_AUTO), ("bf16", L.IMPL_AUTO)])
 @pytest.mark.parametrize("C,shift,linear", [(52, 1, False), (26, 0, False), (104, 1, True), (8, 0, False)])
 def test_ssm_embed_conv_matches_emulator(be, precision, impl, C, shift, linear):
