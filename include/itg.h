@@ -66,7 +66,7 @@ enum itg_impl { ITG_IMPL_AUTO = 0 /* tcgen05 for 16-bit operands (halo-tile kern
                 ITG_IMPL_DIRECT = 1 /* CUDA-core direct conv (any dtype; the on-device cross-check) */,
                 ITG_IMPL_UMMA = 2 /* tcgen05 implicit GEMM, operands streamed per tap (16-bit only) */,
                 ITG_IMPL_TILE = 3 /* tcgen05 persistent halo-tile kernel: k_pad <= 64, n_pad <= 64 (16-bit only) */,
-                ITG_IMPL_PAIR = 4 /* tcgen05 cta_group::2 halo-tile kernel, weights resident: 3x3, k_pad <= 128, n_pad <= 256 (16-bit only) */ };
+                ITG_IMPL_PAIR = 4 /* tcgen05 cta_group::2 halo-tile kernel, weights resident: 3x3 | 1x1, k_pad <= 128, n_pad <= 256 (16-bit only) */ };
 
 enum itg_img_layout { ITG_IMG_MERGED = 0 /* (C, H, W) planar */, ITG_IMG_PATCHES = 1 /* (B, C, P, P) */ };
 

@@ -68,9 +68,11 @@ struct PairParams {
   EpiParams ep;
 };
 
-template <typename T, int F>
+template <typename T, int F, int MODE>
 __global__ void __launch_bounds__(SSM_THREADS, 1)
 conv_pair_kernel(const PairParams p) {
+  static_assert(MODE == ITG_CONV3X3 || MODE == ITG_CONV1X1, "conv_pair: 3x3 or 1x1");
+  constexpr int NTAPS = MODE == ITG_CONV3X3 ? 9 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // the dynamic window starts at the same offset in both CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,7 +115,7 @@ conv_pair_kernel(const PairParams p) {
   {
     const T* wg = reinterpret_cast<const T*>(p.w);
     const int kg = p.k_pad >> 3;
-    const int chunks = 9 * kg * n_half;
+    const int chunks = NTAPS * kg * n_half;
     const uint32_t ws = sbase + PAIR_OFF_W;
     for (int i = threadIdx.x; i < chunks; i += SSM_THREADS) {
       const int j = i % kg, n = (i / kg) % n_half, t = i / (kg * n_half);
@@ -170,11 +172,11 @@ conv_pair_kernel(const PairParams p) {
           for (int ks = 0; ks < 8; ++ks) {
             if (ks < p.ksteps) {
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
+              for (int t = 0; t < NTAPS; ++t) {
 #ifdef ITG_SSM_DBG
                 if (t > 0 && (p.exp & 4)) break;
 #endif
-                const uint32_t shift16 = (uint32_t)((t / 3) * HALO_W + (t % 3));
+                const uint32_t shift16 = MODE == ITG_CONV3X3 ? (uint32_t)((t / 3) * HALO_W + (t % 3)) : (uint32_t)(HALO_W + 1);
                 umma2_f16(d, desc_noswz(ak + (uint32_t)(2 * ks) * (PAIR_PLANE / 16) + shift16, PAIR_PLANE / 16, HALO_W),
                           desc_noswz(w16 + (uint32_t)(2 * ks) * nh16 + (uint32_t)t * tap16, nh16, 8), p.idesc, (ks > 0 || t > 0) ? 1u : 0u);
               }
@@ -196,13 +198,16 @@ conv_pair_kernel(const PairParams p) {
     const int lt = (warp - SSM_WARP_CVT) * 32 + lane;                   // 0..191
     const T* in = reinterpret_cast<const T*>(p.in) + (size_t)p.in_cg_off * 8;
     const uint32_t a_smem = sbase + PAIR_OFF_A;
-    const int row_chunks = HALO_W * p.np, tile_chunks = HALO_H * row_chunks;
+    // (a 1x1 conv reads no neighbours: only the 16 x 8 interior of the halo tile is fetched; the ring around it is never addressed)
+    constexpr int ROWS = MODE == ITG_CONV3X3 ? HALO_H : TILE_H, COLS = MODE == ITG_CONV3X3 ? HALO_W : TILE_W, OFF = MODE == ITG_CONV3X3 ? 0 : 1;
+    const int row_chunks = COLS * p.np, tile_chunks = ROWS * row_chunks;
     uint32_t goff[PAIR_LD_ITERS], soff[PAIR_LD_ITERS];                   // element offset from the halo origin | shared offset, hy << 16, hx << 24 (hy = 31: none)
 #pragma unroll
     for (int i = 0; i < PAIR_LD_ITERS; ++i) {
       const int q = lt + i * PAIR_LOADERS * 32;
-      const int hy = q / row_chunks, r = q - hy * row_chunks;
-      const int hx = r / p.np, c = r - hx * p.np;
+      const int ry = q / row_chunks, r = q - ry * row_chunks;
+      const int rx = r / p.np, c = r - rx * p.np;
+      const int hy = ry + OFF, hx = rx + OFF;
       goff[i] = (uint32_t)((hy * p.in_pitch + hx) * p.in_c + c * 8);
       soff[i] = q < tile_chunks ? ((uint32_t)(c * PAIR_PLANE + (hy * HALO_W + hx) * 16) | ((uint32_t)hy << 16) | ((uint32_t)hx << 24)) : (31u << 16);
     }

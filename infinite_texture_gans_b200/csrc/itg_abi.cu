@@ -496,9 +496,9 @@ int launch_tile(const itg_conv_desc& d, cudaStream_t st) {
   return ITG_OK;
 }
 
-// 3x3 layers with k_pad <= 128 on CTA pairs (conv_pair.cuh): activations read once per tile, weights resident
+// 3x3 and 1x1 layers with k_pad <= 128 on CTA pairs (conv_pair.cuh): activations read once per tile, weights resident
 bool pair_eligible(const itg_conv_desc& d) {
-  if (d.dtype == ITG_F32 || d.mode != ITG_CONV3X3) return false;
+  if (d.dtype == ITG_F32 || (d.mode != ITG_CONV3X3 && d.mode != ITG_CONV1X1)) return false;
   if (d.k_pad > 128) return false;
   if (d.out_img || d.out_f32 || d.mod_x || d.res_kind == ITG_RES_F32) return false;      // final conv / SSM embed / fp32 residual: other kernels
   const int nblocks = (d.n_pad + itg::PAIR_NBLK_MAX - 1) / itg::PAIR_NBLK_MAX;
@@ -519,7 +519,7 @@ bool pair_preferred(const itg_conv_desc& d) {
 
 template <typename T>
 int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
-  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 conv with 16-bit operands, k_pad <= 128, n_pad <= 256 and grid outputs");
+  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 or 1x1 conv with 16-bit operands, k_pad <= 128, n_pad <= 256 and grid outputs");
   itg::PairParams p;
   memset(&p, 0, sizeof(p));
   p.m_h = d.in_h; p.m_w = d.in_w;
@@ -557,25 +557,33 @@ int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
     p.dbg = dbg_buf;
     p.exp = getenv("ITG_TILE_EXP") ? atoi(getenv("ITG_TILE_EXP")) : 0;       // timing experiments (wrong results), debug mode only
   }
-#define ITG_PAIR_LAUNCH(FL)                                                                                           \
+#define ITG_PAIR_LAUNCH(FL, MD)                                                                                       \
   do {                                                                                                                \
     static bool attr_set[MAX_DEVICES] = {false};                                                                      \
     const int dev_ = current_device();                                                                                \
     if (!attr_set[dev_]) {                                                                                            \
-      ITG_CUDA(cudaFuncSetAttribute(itg::conv_pair_kernel<T, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      ITG_CUDA(cudaFuncSetAttribute(itg::conv_pair_kernel<T, FL, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr_set[dev_] = true;                                                                                          \
     }                                                                                                                 \
-    ITG_CUDA(launch_pdl_cluster(itg::conv_pair_kernel<T, FL>, dim3(grid), dim3(itg::SSM_THREADS), smem, st, 2, p));    \
+    ITG_CUDA(launch_pdl_cluster(itg::conv_pair_kernel<T, FL, MD>, dim3(grid), dim3(itg::SSM_THREADS), smem, st, 2, p)); \
   } while (0)
   constexpr int A = itg::EF_ACT, R = itg::EF_RAW, S = itg::EF_RES, G = itg::EF_GENERIC;
-  switch (flags) {
-    case A: ITG_PAIR_LAUNCH(A); break;
-    case R: ITG_PAIR_LAUNCH(R); break;
-    case A | S: ITG_PAIR_LAUNCH(A | S); break;
-    case R | A: ITG_PAIR_LAUNCH(R | A); break;
-    case R | S: ITG_PAIR_LAUNCH(R | S); break;
-    case R | A | S: ITG_PAIR_LAUNCH(R | A | S); break;
-    default: ITG_PAIR_LAUNCH(G); break;
+  if (d.mode == ITG_CONV3X3) {
+    switch (flags) {
+      case A: ITG_PAIR_LAUNCH(A, ITG_CONV3X3); break;
+      case R: ITG_PAIR_LAUNCH(R, ITG_CONV3X3); break;
+      case A | S: ITG_PAIR_LAUNCH(A | S, ITG_CONV3X3); break;
+      case R | A: ITG_PAIR_LAUNCH(R | A, ITG_CONV3X3); break;
+      case R | S: ITG_PAIR_LAUNCH(R | S, ITG_CONV3X3); break;
+      case R | A | S: ITG_PAIR_LAUNCH(R | A | S, ITG_CONV3X3); break;
+      default: ITG_PAIR_LAUNCH(G, ITG_CONV3X3); break;
+    }
+  } else {
+    switch (flags) {
+      case R: ITG_PAIR_LAUNCH(R, ITG_CONV1X1); break;
+      case A: ITG_PAIR_LAUNCH(A, ITG_CONV1X1); break;
+      default: ITG_PAIR_LAUNCH(G, ITG_CONV1X1); break;
+    }
   }
 #undef ITG_PAIR_LAUNCH
   if (dbg_on) {

@@ -95,6 +95,8 @@ CONV_CASES = [
     ("3x3", 40, 24, 128, 208, dict(act=True, res=0, border=L.BORDER_CONSTANT)),
     ("3x3", 150, 90, 52, 26, dict(raw=True, border=L.BORDER_NONE)),
     ("3x3", 9, 7, 26, 26, dict(raw=True, res=0, border=L.BORDER_NONE)),
+    ("1x1", 150, 90, 104, 52, dict(raw=True)),
+    ("1x1", 33, 47, 52, 26, dict(act=True, border=L.BORDER_REPLICATE)),
 ]
 
 
@@ -174,8 +176,8 @@ def test_conv_matches_emulator(be, case, precision, impl):
     dtype = DT[precision]
     if impl == L.IMPL_TILE and (cin > 64 or cout > 64):
         pytest.skip("halo-tile kernel serves k_pad <= 64, n_pad <= 64")
-    if impl == L.IMPL_PAIR and (mode != "3x3" or "img" in ex or k_pad_of(c_store(cin)) > 128 or cout > 256):
-        pytest.skip("CTA-pair kernel serves 3x3 grid-to-grid convs with k_pad <= 128")
+    if impl == L.IMPL_PAIR and (mode == "up" or "img" in ex or k_pad_of(c_store(cin)) > 128 or cout > 256):
+        pytest.skip("CTA-pair kernel serves 3x3 / 1x1 grid-to-grid convs with k_pad <= 128")
     opc = _make_conv(mode, H, W, cin, cout, ex, dtype, impl, seed=H * 1000 + W * 10 + cin + cout)
     opg = _run_both(be, opc, _conv_to_dev)
     _check_conv(opc, opg, dtype)
