@@ -62,11 +62,12 @@ enum itg_border { ITG_BORDER_NONE = 0, ITG_BORDER_REPLICATE = 1, ITG_BORDER_CONS
 enum itg_residual { ITG_RES_NONE = 0, ITG_RES_GRID = 1 /* framed grid tensor, operand dtype */,
                     ITG_RES_F32 = 2 /* unframed fp32 NHWC */ };
 
-enum itg_impl { ITG_IMPL_AUTO = 0 /* tcgen05 for 16-bit operands (halo-tile kernel when eligible), direct for fp32 */,
+enum itg_impl { ITG_IMPL_AUTO = 0 /* tcgen05 kernels: pair / halo-tile / streaming for 16-bit operands, split-precision for fp32 */,
                 ITG_IMPL_DIRECT = 1 /* CUDA-core direct conv (any dtype; the on-device cross-check) */,
                 ITG_IMPL_UMMA = 2 /* tcgen05 implicit GEMM, operands streamed per tap (16-bit only) */,
                 ITG_IMPL_TILE = 3 /* tcgen05 persistent halo-tile kernel: k_pad <= 64, n_pad <= 64 (16-bit only) */,
-                ITG_IMPL_PAIR = 4 /* tcgen05 cta_group::2 halo-tile kernel, weights resident: 3x3 | 1x1, k_pad <= 128, n_pad <= 256 (16-bit only) */ };
+                ITG_IMPL_PAIR = 4 /* tcgen05 cta_group::2 halo-tile kernel, weights resident: 3x3 | 1x1, k_pad <= 128, n_pad <= 256 (16-bit only) */,
+                ITG_IMPL_SPLIT = 5 /* fp32 tensors on tensor cores: operands split into two fp16 terms, three tcgen05.mma per step (fp32 only) */ };
 
 enum itg_img_layout { ITG_IMG_MERGED = 0 /* (C, H, W) planar */, ITG_IMG_PATCHES = 1 /* (B, C, P, P) */ };
 

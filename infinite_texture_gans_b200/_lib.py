@@ -20,7 +20,7 @@ F32, F16, BF16 = 0, 1, 2
 CONV3X3, CONV1X1, UPCONV = 0, 1, 2
 BORDER_NONE, BORDER_REPLICATE, BORDER_CONSTANT = 0, 1, 2
 RES_NONE, RES_GRID, RES_F32 = 0, 1, 2
-IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA, IMPL_TILE, IMPL_PAIR = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA, IMPL_TILE, IMPL_PAIR, IMPL_SPLIT = 0, 1, 2, 3, 4, 5
 IMG_MERGED, IMG_PATCHES = 0, 1
 
 DTYPE_OF = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}

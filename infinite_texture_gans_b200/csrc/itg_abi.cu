@@ -17,6 +17,7 @@
 #include "ssm_fused.cuh"
 #include "ssm_fused2.cuh"
 #include "conv_pair.cuh"
+#include "conv_split.cuh"
 
 namespace {
 
@@ -212,6 +213,24 @@ int launch_direct(const itg_conv_desc& d, cudaStream_t st) {
   p.ep = make_epi(d);
   dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(d.n_pad / itg::DIRECT_NB), d.mode == ITG_UPCONV ? 4u : 1u);
   itg::conv_direct_kernel<T><<<grid, 128, 0, st>>>(p);
+  ITG_CUDA(cudaGetLastError());
+  return ITG_OK;
+}
+
+// exact mode on tensor cores (conv_split.cuh): fp32 tensors, every operand as two fp16 terms, three MMAs per step
+int launch_split(const itg_conv_desc& d, cudaStream_t st) {
+  itg::SplitParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = reinterpret_cast<const float*>(d.in); p.in_h = d.in_h; p.in_w = d.in_w; p.in_pitch = d.in_pitch ? d.in_pitch : d.in_w + 2;
+  p.in_c = d.in_c; p.in_c_off = d.in_c_off; p.k = d.k;
+  p.w = reinterpret_cast<const float*>(d.w); p.n_pad = d.n_pad; p.k_pad = d.k_pad; p.mode = d.mode;
+  p.tw_log2 = pick_tw_log2(d.in_w);
+  const int tw = 1 << p.tw_log2, th = 128 >> p.tw_log2;
+  p.tiles_x = (d.in_w + tw - 1) / tw;
+  const int tiles_y = (d.in_h + th - 1) / th;
+  p.ep = make_epi(d);
+  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)((d.n_pad + itg::SPLIT_NB - 1) / itg::SPLIT_NB), d.mode == ITG_UPCONV ? 4u : 1u);
+  itg::conv_split_kernel<<<grid, 128, itg::SPLIT_SMEM, st>>>(p);
   ITG_CUDA(cudaGetLastError());
   return ITG_OK;
 }
@@ -709,7 +728,11 @@ int itg_conv_fwd(const itg_conv_desc* desc, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int impl = d.impl;
   if (impl == ITG_IMPL_AUTO)
-    impl = (d.dtype == ITG_F32) ? ITG_IMPL_DIRECT : (pair_preferred(d) ? ITG_IMPL_PAIR : (tile_eligible(d) ? ITG_IMPL_TILE : ITG_IMPL_UMMA));
+    impl = (d.dtype == ITG_F32) ? ITG_IMPL_SPLIT : (pair_preferred(d) ? ITG_IMPL_PAIR : (tile_eligible(d) ? ITG_IMPL_TILE : ITG_IMPL_UMMA));
+  if (impl == ITG_IMPL_SPLIT) {
+    if (d.dtype == ITG_F32) return launch_split(d, st);
+    return fail(ITG_ERR_UNSUPPORTED, "conv: the split-precision path takes fp32 tensors (16-bit tensors run the fp16 / bf16 kernels)");
+  }
   if (impl == ITG_IMPL_PAIR) {
     if (d.dtype == ITG_F16) return launch_pair<__half>(d, st);
     if (d.dtype == ITG_BF16) return launch_pair<__nv_bfloat16>(d, st);

@@ -32,7 +32,8 @@ from .ops import AttentionOp, ConvOp, Grid, SsmOp, c_store
 
 PRECISIONS = {
     # name: (torch dtype, conv implementation)
-    "fp32": (torch.float32, L.IMPL_DIRECT),     # exact mode: CUDA-core fp32 (the <= 1e-3 gate)
+    "fp32": (torch.float32, L.IMPL_SPLIT),      # exact mode (the <= 1e-3 gate) on tensor cores: fp32 tensors, operands as two fp16 terms, 3 MMAs per step
+    "fp32-direct": (torch.float32, L.IMPL_DIRECT),   # exact mode on CUDA cores: cross-check of the split-precision kernel
     "fp16": (torch.float16, L.IMPL_AUTO),       # tcgen05 kind::f16, fp16 operands / fp32 accumulate
     "fp16-stream": (torch.float16, L.IMPL_UMMA),     # force the per-tap streaming kernel everywhere, SSM as two launches (A/B comparison)
     "fp16-direct": (torch.float16, L.IMPL_DIRECT),   # on-device cross-check of the tcgen05 kernel

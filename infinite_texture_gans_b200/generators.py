@@ -25,7 +25,7 @@ class ResidualPatchGenerator(nn.Module):
     """See models/generators.py:6-23 for the argument meanings.
 
     Extra keyword (defaults keep the reference behaviour):
-      precision : 'fp16' (tcgen05 16-bit mode, default: image within 2e-2 of the fp32 reference) or 'fp32' (exact CUDA-core mode, within 1e-3).
+      precision : 'fp16' (tcgen05 16-bit mode, default: image within 2e-2 of the fp32 reference) or 'fp32' (exact mode, within 1e-3: fp32 tensors, split-precision tensor-core convs).
     """
 
     def __init__(self, z_dim=128, G_ch=64, base_res=4, n_layers_G=4, attention=True, img_ch=3, leak=0, SN=False,

@@ -166,10 +166,10 @@ def _check_conv(opc: ConvOp, opg: ConvOp, dtype):
         _cmp(opc.name + ".act", a, b, dtype)
 
 
-@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA),
+@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp32", L.IMPL_SPLIT), ("fp16", L.IMPL_DIRECT), ("fp16", L.IMPL_UMMA),
                                             ("bf16", L.IMPL_UMMA), ("fp16", L.IMPL_TILE), ("bf16", L.IMPL_TILE),
                                             ("fp16", L.IMPL_PAIR), ("bf16", L.IMPL_PAIR)],
-                         ids=["fp32-direct", "fp16-direct", "fp16-umma", "bf16-umma", "fp16-tile", "bf16-tile", "fp16-pair", "bf16-pair"])
+                         ids=["fp32-direct", "fp32-split", "fp16-direct", "fp16-umma", "bf16-umma", "fp16-tile", "bf16-tile", "fp16-pair", "bf16-pair"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}")
 def test_conv_matches_emulator(be, case, precision, impl):
     mode, H, W, cin, cout, ex = case
@@ -209,7 +209,7 @@ def test_auto_kernel_choice_does_not_depend_on_the_grid_size(be, cin, cout):
     assert torch.equal(win, full[wy:wy + wh, wx:wx + ww])
 
 
-@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp16", L.IMPL_AUTO), ("bf16", L.IMPL_AUTO)])
+@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp32", L.IMPL_SPLIT), ("fp16", L.IMPL_AUTO), ("bf16", L.IMPL_AUTO)])
 @pytest.mark.parametrize("C,shift,linear", [(52, 1, False), (26, 0, False), (104, 1, True), (8, 0, False)])
 def test_ssm_embed_conv_matches_emulator(be, precision, impl, C, shift, linear):
     """The SSM pair: valid conv on a window of the hidden map + modulation epilogue (layers.py:228-234)."""
