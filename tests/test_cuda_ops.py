@@ -363,8 +363,8 @@ def test_halo_gather_indexing_is_bit_exact_vs_reference_local_padder(be, mode_na
     tests/golden/localpad.npz holds integer-coded patch batches and the (B, C, r+2, r+2) windows the UNMODIFIED
     reference LocalPadder produced for them.  A 3x3 conv whose weight for output column t*C+c is the delta at tap t,
     channel c copies the gathered neighbourhood to its output: out[y, x, t*C + c] = window[c, y%r + t//3, x%r + t%3].
-    fp32 CUDA-core kernel on the golden integers; tcgen05 halo-tile and streaming kernels (fp16 holds integers < 2048
-    exactly) on the same values reduced mod 2039, all compared exactly."""
+    fp32 CUDA-core and split-precision kernels on the golden integers; tcgen05 halo-tile, streaming and CTA-pair kernels (fp16 holds
+    integers < 2048 exactly) on the same values reduced mod 2039, all compared exactly."""
     import os
     import numpy as np
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "localpad.npz"))
@@ -385,8 +385,8 @@ def test_halo_gather_indexing_is_bit_exact_vs_reference_local_padder(be, mode_na
         for t in range(9):
             ref[py * r:(py + 1) * r, px * r:(px + 1) * r, t * C:(t + 1) * C] = \
                 win[p, :, t // 3:t // 3 + r, t % 3:t % 3 + r].permute(1, 2, 0)
-    for precision, impl, modulo in (("fp32", L.IMPL_DIRECT, None), ("fp16", L.IMPL_TILE, 2039), ("fp16", L.IMPL_UMMA, 2039),
-                                    ("bf16", L.IMPL_TILE, 251)):
+    for precision, impl, modulo in (("fp32", L.IMPL_DIRECT, None), ("fp32", L.IMPL_SPLIT, None), ("fp16", L.IMPL_TILE, 2039),
+                                    ("fp16", L.IMPL_UMMA, 2039), ("fp16", L.IMPL_PAIR, 2039), ("bf16", L.IMPL_TILE, 251)):
         dtype = DT[precision]
         src_v = merged if modulo is None else torch.remainder(merged, modulo)
         ref_v = ref if modulo is None else torch.remainder(ref, modulo)
