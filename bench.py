@@ -325,6 +325,27 @@ def run_workload(name, args, ctx, steps, warmup, *, with_cpu, with_parity, profi
     else:
         sampler.step()
     torch.cuda.synchronize()
+    # N > 1: the first patch row BELOW the band-0 / band-1 seam (rank 1's output, its top halo rows came from rank 0 over NVLink) against the
+    # CPU oracle on a noise window that straddles the seam (three patch rows of each band, two-patch margin) -- checker use of oracle/
+    seam = None
+    if world > 1 and with_parity:
+        seam_t = torch.full((1,), -1.0, device=dev)
+        if rank == 1:
+            from oracle import itg_oracle as O
+            from oracle import window as OW
+            ocfg = O.GenCfg(**kw)
+            cols = min(5, tw)
+            zc, mc = OW.crop_noise(ocfg, z_full, maps_full, r0 - 3, r0 + 3, 0, cols)
+            with torch.no_grad():
+                ref = O.forward_merged(sd, ocfg, zc, mc)
+            lc = cols if cols == tw else cols - 2
+            got = plan.out[:, :, :P, :lc * P].detach().float().cpu()
+            seam_t[0] = (got - ref[:, :, 3 * P:4 * P, :lc * P]).abs().max().item()
+        dist.all_reduce(seam_t, op=dist.ReduceOp.MAX)
+        tol = 2e-2 if args.precision != "fp32" else 1e-3
+        seam = {"max_abs": seam_t.item(), "tolerance": tol, "ok": 0.0 <= seam_t.item() <= tol,
+                "what": f"patch row {r0 if rank == 1 else th} (first row of band 1) x patch columns [0, {min(5, tw) if min(5, tw) == tw else min(5, tw) - 2}) against the oracle on the "
+                        "noise window of patch rows [seam - 3, seam + 3)"}
     if rank == 0:
         total_flops = flops_per_patch(cfg) * th * tw
         if world == 1:
@@ -379,6 +400,9 @@ def run_workload(name, args, ctx, steps, warmup, *, with_cpu, with_parity, profi
             parity = {"max_abs": err, "tolerance": 2e-2 if args.precision != "fp32" else 1e-3, "ok": err <= (2e-2 if args.precision != "fp32" else 1e-3),
                       "against": "oracle/itg_oracle.py forward_merged (CPU fp32) on the cropped noise window", "window_patches": list(win),
                       "trusted_patches": list(trusted), "oracle_s": time.perf_counter() - t0}
+            if seam is not None:
+                parity["seam"] = seam
+                parity["ok"] = parity["ok"] and seam["ok"]
         if with_cpu and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             v, threads, sample, _ = cpu_reference_rate(kw, th, tw, sd, budget_s=15.0)

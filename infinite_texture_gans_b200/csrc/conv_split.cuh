@@ -9,7 +9,10 @@
 // Per (tap, 16-channel chunk): every thread fetches its pixel's 16 channels (the local-padding gather is the tap offset into the framed
 // tensor), splits them and writes the two K-major no-swizzle operand tiles; the weight chunk is split the same way; one thread issues
 // the three MMAs and commits to the stage's mbarrier.  Two stages; several CTAs per SM (28 KB of shared memory, 64 TMEM columns each)
-// hide the load latency.  Not tuned: it replaces a CUDA-core kernel, not one of the fp16 kernels.
+// hide the load latency.  Not tuned: it replaces a CUDA-core kernel, not one of the fp16 kernels.  Measured (cfg2 per pass: 3.9 ms against 7.8 ms
+// on CUDA cores; SSM windows 3.2x): the thin full-resolution layers are bound by the LSU's line requests of the per-tap fp32 gathers
+// (64-byte pixels: 16 lines per warp load), exactly like the direct kernel -- 32 channels per step with the next step's loads in flight, and a
+// persistent variant packing two taps per step, changed nothing / were slower.  The next step would be the halo-tile load of conv_tile.cuh.
 #pragma once
 #include "ssm_fused.cuh"
 
