@@ -6,13 +6,14 @@
 // (3x3, 1x1, folded up-sampling conv), any K, windows into wider buffers, residuals, SSM modulation, image / pre-tanh outputs.
 //
 // One CTA = 128 output-grid pixels (TH x TW tile) x <= 64 GEMM columns x one up-sampling phase; thread r owns pixel r (= TMEM lane r).
-// Per (tap, 16-channel chunk): every thread fetches its pixel's 16 channels (the local-padding gather is the tap offset into the framed
-// tensor), splits them and writes the two K-major no-swizzle operand tiles; the weight chunk is split the same way; one thread issues
+// Per (tap, 16-channel chunk): the threads fetch the tile's 128 x 16 values in memory order (the local-padding gather is the tap offset into
+// the framed tensor), split them and writes the two K-major no-swizzle operand tiles; the weight chunk is split the same way; one thread issues
 // the three MMAs and commits to the stage's mbarrier.  Two stages; several CTAs per SM (28 KB of shared memory, 64 TMEM columns each)
-// hide the load latency.  Not tuned: it replaces a CUDA-core kernel, not one of the fp16 kernels.  Measured (cfg2 per pass: 3.9 ms against 7.8 ms
-// on CUDA cores; SSM windows 3.2x): the thin full-resolution layers are bound by the LSU's line requests of the per-tap fp32 gathers
-// (64-byte pixels: 16 lines per warp load), exactly like the direct kernel -- 32 channels per step with the next step's loads in flight, and a
-// persistent variant packing two taps per step, changed nothing / were slower.  The next step would be the halo-tile load of conv_tile.cuh.
+// hide the load latency.  Not tuned: it replaces a CUDA-core kernel, not one of the fp16 kernels.  Measured: cfg2 3.4 ms per pass against
+// 7.8 ms on CUDA cores (0.38 ms of both is the fp32 attention kernel), a 15 x 15-patch SSM window 17.9 against 77.1 ms.  The thin
+// full-resolution layers are bound by the LSU's line requests of the per-tap fp32 gathers: fetching in memory order instead of one pixel
+// per thread gave 3.9 -> 3.4 / 23.9 -> 17.9 ms, while 32 channels per step with the next step's loads in flight, and a persistent variant
+// packing two taps per step, changed nothing / were slower.  The next step would be the halo-tile load of conv_tile.cuh.
 #pragma once
 #include "ssm_fused.cuh"
 
@@ -87,17 +88,27 @@ __global__ void __launch_bounds__(128) conv_split_kernel(const SplitParams p) {
   for (int t = 0; t < ntaps; ++t) {
     int dy, dx, wt;
     tap_offsets(p.mode, phase, t, dy, dx, wt);
-    const float* a_ptr = p.in + grid_off_pitch(valid ? y + dy : 0, valid ? x + dx : 0, p.in_pitch, p.in_c, p.in_c_off);
+    // gather in memory order: thread r fetches 8-channel group (r & 1) of pixels (r >> 1) and 64 + (r >> 1) of the tile -- a warp
+    // instruction covers 16 consecutive pixels x 64 contiguous bytes instead of 32 pixels x 16 bytes (a quarter of the line requests)
+    const float* a_src[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int px = i * 64 + (r >> 1);
+      const int py = (tile / p.tiles_x) * (128 >> p.tw_log2) + (px >> p.tw_log2), pxx = (tile % p.tiles_x) * tw + (px & (tw - 1));
+      a_ok[i] = (py < p.in_h) && (pxx < p.in_w);
+      a_src[i] = p.in + grid_off_pitch(a_ok[i] ? py + dy : 0, a_ok[i] ? pxx + dx : 0, p.in_pitch, p.in_c, p.in_c_off) + 8 * (r & 1);
+    }
     const float* w_tap = p.w + ((size_t)wt * p.n_pad + n0) * (size_t)p.k_pad;
     for (int k0 = 0; k0 < p.k; k0 += 16, ++it) {
       const int s = it & 1;
       const uint32_t a_hi = stages + (uint32_t)(s * SPLIT_STAGE), a_lo = a_hi + SPLIT_A_BYTES;
       const uint32_t b_hi = a_lo + SPLIT_A_BYTES, b_lo = b_hi + SPLIT_B_BYTES;
-      // this pixel's 16 channels (k and the channel offsets are multiples of 8; channels beyond k read as zeros)
+      // 8 channels of two pixels (k and the channel offsets are multiples of 8; channels beyond k read as zeros)
       float a[2][8];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        if (valid && k0 + 8 * j < p.k) load8(a_ptr + k0 + 8 * j, a[j]);
+        if (a_ok[j] && k0 + 8 * (r & 1) < p.k) load8(a_src[j] + k0, a[j]);
         else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) a[j][i] = 0.f;
@@ -117,8 +128,8 @@ __global__ void __launch_bounds__(128) conv_split_kernel(const SplitParams p) {
       for (int j = 0; j < 2; ++j) {
         uint4 hi, lo;
         split8(a[j], hi, lo);
-        sts128(a_hi + (uint32_t)(j * 2048 + r * 16), hi.x, hi.y, hi.z, hi.w);
-        sts128(a_lo + (uint32_t)(j * 2048 + r * 16), lo.x, lo.y, lo.z, lo.w);
+        sts128(a_hi + (uint32_t)((r & 1) * 2048 + (j * 64 + (r >> 1)) * 16), hi.x, hi.y, hi.z, hi.w);
+        sts128(a_lo + (uint32_t)((r & 1) * 2048 + (j * 64 + (r >> 1)) * 16), lo.x, lo.y, lo.z, lo.w);
       }
       if (w_ok) {
         uint4 hi, lo;
