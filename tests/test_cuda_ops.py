@@ -183,6 +183,31 @@ def test_conv_matches_emulator(be, case, precision, impl):
     _check_conv(opc, opg, dtype)
 
 
+@pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp32", L.IMPL_SPLIT), ("fp16", L.IMPL_UMMA), ("fp16", L.IMPL_TILE),
+                                            ("fp16", L.IMPL_PAIR)], ids=["direct", "split", "umma", "tile", "pair"])
+@pytest.mark.parametrize("mode,H,W,cin,cout", [("3x3", 33, 47, 52, 26), ("1x1", 17, 9, 64, 64), ("3x3", 130, 21, 26, 13)])
+def test_conv_writes_stay_inside_their_tensors(be, precision, impl, mode, H, W, cin, cout):
+    """Partial tiles, odd tile counts, padded GEMM columns: nothing is written outside the output tensors (guard zones on both sides stay
+    intact; compute-sanitizer is not available on the GPU pool)."""
+    dtype = DT[precision]
+    opc = _make_conv(mode, H, W, cin, cout, dict(raw=True, act=True, res=0, border=L.BORDER_REPLICATE), dtype, impl, seed=H + W + cin)
+    op = _conv_to_dev(opc)
+    guard, canary = 4096, 123.0
+    outs = {}
+    for name in ("out_raw", "out_act"):
+        g = getattr(op, name)
+        n = g.buf.numel()
+        big = torch.full((n + 2 * guard,), canary, dtype=dtype, device="cuda")
+        setattr(op, name, Grid(big[guard:guard + n].view_as(g.buf), g.h, g.w, g.c))
+        outs[name] = big
+    be.conv(op)
+    torch.cuda.synchronize()
+    for name, big in outs.items():
+        assert bool((big[:guard] == canary).all()) and bool((big[-guard:] == canary).all()), f"{name}: write outside the tensor"
+    EmulatorBackend().conv(opc)
+    _check_conv(opc, op, dtype)
+
+
 @pytest.mark.parametrize("cin,cout", [(104, 52), (52, 26), (26, 26), (208, 104), (13, 13)])
 def test_auto_kernel_choice_does_not_depend_on_the_grid_size(be, cin, cout):
     """A row band and the whole texture must run the same kernel for the same layer: the same pixels computed as part of a large grid and
