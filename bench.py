@@ -361,7 +361,7 @@ def run_workload(name, args, ctx, steps, warmup, *, with_cpu, with_parity, profi
             if sf:
                 by["ssm_fused2_kernel (StochasticSpatialModulation, cta_group::2)"] = {"ms": fams["ssm"], "tflops": sf / (fams["ssm"] / 1e3) / 1e12,
                                                                                       "frac": sf / (fams["ssm"] / 1e3) / 1e12 / bf16_peak}
-            by["conv_umma_kernel + conv_tile_kernel (conv2d_lp / 1x1 launches)"] = {
+            by["conv_pair_kernel + conv_tile_kernel + conv_umma_kernel (conv2d_lp / 1x1 launches)"] = {
                 "ms": fams.get("conv", 0.0), "tflops": (conv_alg - sf) / (max(fams.get("conv", 0.0), 1e-9) / 1e3) / 1e12,
                 "frac": (conv_alg - sf) / (max(fams.get("conv", 0.0), 1e-9) / 1e3) / 1e12 / bf16_peak}
             traffic = None

@@ -40,7 +40,7 @@ echo "## ncu launch list: share of each kernel (cold-cache, serialised; compare 
 echo
 python tools/ncu_summary.py launches gpurun_out/${R}_launches_cfg3.csv
 echo
-echo "(\`ssm_fused2_kernel\`: StochasticSpatialModulation on CTA pairs, \`tcgen05.mma.cta_group::2\`; \`conv_pair_kernel<T, F>\`: 3x3 convs with 64 <= k_pad <= 128 on CTA pairs; \`conv_tile_kernel<T, F, MODE>\`: F = epilogue flags RES=1 RAW=2 ACT=4 IMG=8; MODE 0 = 3x3, 1 = 1x1, 2 = folded up-sampling conv; \`conv_umma_kernel<T, F>\` likewise. The FillFunctor launch is bench.py's 256 MiB L2 flush.)"
+echo "(\`ssm_fused2_kernel\`: StochasticSpatialModulation on CTA pairs, \`tcgen05.mma.cta_group::2\`; \`conv_pair_kernel<T, F, MODE>\`: 3x3 (MODE 0) and 1x1 (MODE 1) convs with 64 <= k_pad <= 128 on CTA pairs; \`conv_tile_kernel<T, F, MODE>\`: F = epilogue flags RES=1 RAW=2 ACT=4 IMG=8; MODE 0 = 3x3, 1 = 1x1, 2 = folded up-sampling conv; \`conv_umma_kernel<T, F>\` likewise. The FillFunctor launch is bench.py's 256 MiB L2 flush.)"
 echo
 echo "## CUDA-event time per launch of one step (bench.py, eager launches, L2 warm)"
 echo
