@@ -28,6 +28,7 @@ ap.add_argument("--rows", type=int, default=513)
 ap.add_argument("--cols", type=int, default=513)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--device-noise", action="store_true", help="draw every band's latent grid on its GPU (counter-based Philox field, itg_noise_normal) instead of on the host RNG")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -50,10 +51,14 @@ r0, th, tw = starts[rank], heights[rank], a.cols
 # every rank draws the same full latent grid (same seed) and keeps its band (+ the 1-px ring rows it shares with its neighbours)
 t0 = time.time()
 g = torch.Generator().manual_seed(4321)
-zb = torch.empty((cfg.z_dim, th * b + 2, tw * b + 2), dtype=torch.float32)
 full_rows = a.rows * b + 2
 chunk = 64                                              # rows of the full grid drawn per call: bounded host memory
-for y0 in range(0, full_rows, chunk):
+if a.device_noise:
+    zb = itg.utils.draw_noise_device(cfg, a.rows, a.cols, 4321, rows=(r0, r0 + th), device=dev)[0]
+    torch.cuda.synchronize()
+else:
+    zb = torch.empty((cfg.z_dim, th * b + 2, tw * b + 2), dtype=torch.float32)
+for y0 in range(0, full_rows if not a.device_noise else 0, chunk):
     n = min(chunk, full_rows - y0)
     blk = torch.randn(cfg.z_dim, n, tw * b + 2, generator=g)
     lo, hi = max(y0, r0 * b), min(y0 + n, (r0 + th) * b + 2)
@@ -108,7 +113,9 @@ if world > 1:
         wr0 = heights[0] - 3
         gz = torch.Generator().manual_seed(4321)
         zw = torch.empty((1, cfg.z_dim, 6 * b + 2, (ncol + 2) * b + 2))
-        for y0 in range(0, full_rows, chunk):
+        if a.device_noise:
+            zw = itg.utils.draw_noise_device(cfg, a.rows, a.cols, 4321, rows=(wr0, wr0 + 6), device=dev)[0][:, :, :(ncol + 2) * b + 2].unsqueeze(0).contiguous()
+        for y0 in range(0, full_rows if not a.device_noise else 0, chunk):
             n = min(chunk, full_rows - y0)
             blk = torch.randn(cfg.z_dim, n, tw * b + 2, generator=gz)
             lo, hi = max(y0, wr0 * b), min(y0 + n, (wr0 + 6) * b + 2)
