@@ -14,7 +14,7 @@
 //     shared offset) table is tile-independent and lives in registers;
 //   * the weights of all taps for the CTA's half of the pair's <= 64 GEMM columns (72 KB) stay in shared memory for the whole launch:
 //     in steady state the kernel reads each activation once (+ halo) and writes its outputs; wider layers run as column blocks;
-//   * whole tiles are handed over through a ring of 3 (K = 128) / 6 (K = 64) / 8 (K = 32) slots, all but one in flight per loader warp;
+//   * whole tiles are handed over through a ring of 3 (K = 128) / 6 (K = 64) / 8 (K = 32) slots, up to three in flight per loader warp;
 //   * one instruction covers M = 256 pixels (both CTAs' tiles) x N columns: half the instructions of the single-CTA kernels for the
 //     same tile, each CTA reading its own A and only its half of B;
 //   * the leader CTA's MMA warp issues from an elect-guarded block (uniform-datapath descriptors, literal offsets); commits are
