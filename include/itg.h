@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ITG_ABI_VERSION 2
+#define ITG_ABI_VERSION 3
 
 enum itg_status {
   ITG_OK = 0,
@@ -126,6 +126,16 @@ typedef struct itg_conv_desc {
   int32_t img_c;        /* image channels (generators.py:83) */
   int32_t img_layout;   /* itg_img_layout */
   int32_t patch;        /* P, for ITG_IMG_PATCHES */
+
+  /* Optional second input (ABI v3): the 1x1 shortcut of a residual block folded into its conv2 (layers.py:294-299, 319-320) --
+   * result = conv(in, w) + conv1x1(in2, w2) + bias, one accumulator, no intermediate tensor.  ITG_CONV3X3 on the CTA-pair kernel
+   * only (ITG_IMPL_PAIR, or ITG_IMPL_AUTO when the layer is eligible); NULL = off. */
+  const void* in2;      /* framed grid tensor of the same interior size as `in` */
+  int32_t in2_c;        /* its storage channels (multiple of 8) */
+  int32_t in2_c_off;    /* first channel of the slice read (multiple of 8) */
+  int32_t k2;           /* channels contracted (multiple of 8, <= k2_pad <= 128) */
+  const void* w2;       /* [1][n_pad][k2_pad], operand dtype */
+  int32_t k2_pad;
 } itg_conv_desc;
 
 /* Library / ABI version (ITG_ABI_VERSION). */

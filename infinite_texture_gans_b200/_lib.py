@@ -46,6 +46,7 @@ class ConvDesc(C.Structure):
         ("out_raw", C.c_void_p), ("out_act", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("leak", C.c_float), ("act_linear", C.c_int32), ("out_f32", C.c_void_p), ("out_img", C.c_void_p),
         ("img_c", C.c_int32), ("img_layout", C.c_int32), ("patch", C.c_int32),
+        ("in2", C.c_void_p), ("in2_c", C.c_int32), ("in2_c_off", C.c_int32), ("k2", C.c_int32), ("w2", C.c_void_p), ("k2_pad", C.c_int32),
     ]
 
 

@@ -14,7 +14,9 @@
 //     shared offset) table is tile-independent and lives in registers;
 //   * the weights of all taps for the CTA's half of the pair's <= 64 GEMM columns (72 KB) stay in shared memory for the whole launch:
 //     in steady state the kernel reads each activation once (+ halo) and writes its outputs; wider layers run as column blocks;
-//   * whole tiles are handed over through a ring of 3 (K = 128) / 6 (K = 64) / 8 (K = 32) slots, up to three in flight per loader warp;
+//   * whole tiles are handed over through a ring of 3 (K = 104) / 5 (K = 64) / 8 (K = 32) slots, up to three in flight per loader warp;
+//   * optional second input (itg_conv_desc.in2): the block's 1x1 shortcut folded into its conv2 -- the loaders also fetch the tile interior
+//     of the shortcut's input into further planes of the slot, the MMA warp appends its k-steps (centre tap, weights of a tenth tap);
 //   * one instruction covers M = 256 pixels (both CTAs' tiles) x N columns: half the instructions of the single-CTA kernels for the
 //     same tile, each CTA reading its own A and only its half of B;
 //   * the leader CTA's MMA warp issues from an elect-guarded block (uniform-datapath descriptors, literal offsets); commits are
@@ -32,18 +34,19 @@ constexpr int PAIR_KG_MAX = 16;                                        // 8-chan
 constexpr int PAIR_NH = 32;                                            // weight rows parked per CTA (row pitch of the weight image)
 constexpr int PAIR_NBLK_MAX = 2 * PAIR_NH;                             // GEMM columns per CTA pair
 constexpr int PAIR_PLANE = PLANE_BYTES + 16;                           // plane pitch 2896 B = 16 (mod 128), see TILE_PLANE
-constexpr int PAIR_A_PLANES = 48;                                      // activation ring: 3 x 16 | 6 x 8 | 8 x 4 planes
+constexpr int PAIR_A_PLANES = 45;                                      // activation ring: 3 x 14 | 5 x 8 | 8 x 4 planes (2 x 16 for K = 128 exactly)
+constexpr int PAIR_W_TAPS = 10;                                        // nine taps + the folded 1x1 shortcut
 constexpr int PAIR_MAX_SLOTS = 8;
 constexpr int PAIR_HDR = 1024;                                         // barriers | at 256: bias, scale, shift of the pair's 64 columns (fp32)
 constexpr int PAIR_OFF_VEC = 256;
 constexpr int PAIR_OFF_STAGE = PAIR_HDR;                               // 8 epilogue warps x [32 pixels][64 B]: transposition buffer of the coalesced stores
 constexpr int PAIR_OFF_W = PAIR_OFF_STAGE + 8 * 2048;                  // [tap 9][k-group 16, kg used][32 rows, n_half used][16 B]
-constexpr int PAIR_OFF_A = PAIR_OFF_W + 9 * PAIR_KG_MAX * PAIR_NH * 16;
+constexpr int PAIR_OFF_A = PAIR_OFF_W + PAIR_W_TAPS * PAIR_KG_MAX * PAIR_NH * 16;
 constexpr int PAIR_LOADERS = 6;                                        // warps 8..13
-constexpr int PAIR_LD_ITERS = (HALO_PX * PAIR_KG_MAX + PAIR_LOADERS * 32 - 1) / (PAIR_LOADERS * 32);      // 16-byte chunks per loader thread and tile: 15
+constexpr int PAIR_LD_ITERS = 16;                                      // 16-byte chunks per loader thread and tile (launch_pair checks the count)
 static_assert(PAIR_OFF_A % 128 == 0, "operand alignment");
 
-constexpr int PAIR_SMEM = PAIR_OFF_A + PAIR_A_PLANES * PAIR_PLANE + 1024;     // 231 168 B: one CTA per SM
+constexpr int PAIR_SMEM = PAIR_OFF_A + PAIR_A_PLANES * PAIR_PLANE + 1024;     // 230 672 B: one CTA per SM
 static_assert(PAIR_SMEM <= 227 * 1024, "shared memory budget");
 
 struct PairParams {
@@ -54,7 +57,12 @@ struct PairParams {
   int buf_h, buf_w;        // buffer extent in pixels (interior + frame)
   int in_cg_off;           // first 8-channel group of the input slice
   int np;                  // 8-channel planes loaded per tile: k / 8 (<= 16)
-  int slot_planes;         // planes per ring slot: 2 * ksteps
+  const void* in2;         // optional second input (1x1 shortcut folded into a 3x3 conv): same geometry as `in`; NULL = off
+  int in2_c, in2_cg_off;
+  int np2, ksteps2;        // its planes per tile (interior only) and K = 16 steps; the planes follow the first input's 2 * ksteps in the slot
+  const void* w2;          // [1][n_pad][k2_pad]
+  int k2_pad;
+  int slot_planes;         // planes per ring slot: 2 * (ksteps + ksteps2)
   int nring;               // ring slots (<= 8)
   int ksteps;              // K = 16 steps per tap
   const void* w;           // [9][n_pad][k_pad] operand dtype
@@ -124,10 +132,22 @@ conv_pair_kernel(const PairParams p) {
       if (ng < p.n_pad) v = *reinterpret_cast<const uint4*>(wg + ((size_t)t * p.n_pad + ng) * p.k_pad + j * 8);
       sts128(ws + (uint32_t)(((t * PAIR_KG_MAX + j) * PAIR_NH + n) * 16), v.x, v.y, v.z, v.w);
     }
-    const int pad_planes = p.slot_planes - p.np;
+    if (MODE == ITG_CONV3X3 && p.in2 != nullptr) {                     // the shortcut's weights: tap 9 of the image
+      const T* w2g = reinterpret_cast<const T*>(p.w2);
+      const int kg2 = p.k2_pad >> 3;
+      for (int i = threadIdx.x; i < kg2 * n_half; i += SSM_THREADS) {
+        const int j = i % kg2, n = i / kg2;
+        const int ng = n0 + (int)rank * n_half + n;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ng < p.n_pad) v = *reinterpret_cast<const uint4*>(w2g + (size_t)ng * p.k2_pad + j * 8);
+        sts128(ws + (uint32_t)(((9 * PAIR_KG_MAX + j) * PAIR_NH + n) * 16), v.x, v.y, v.z, v.w);
+      }
+    }
+    const int pad1 = 2 * p.ksteps - p.np, pad2 = 2 * p.ksteps2 - p.np2, pad_planes = pad1 + pad2;      // 0 or 1 each
     for (int i = threadIdx.x; i < p.nring * pad_planes * (PAIR_PLANE / 16); i += SSM_THREADS) {
       const int c = i % (PAIR_PLANE / 16), r = i / (PAIR_PLANE / 16);
-      const int s = r / pad_planes, j = p.np + r % pad_planes;
+      const int s = r / pad_planes, w = r % pad_planes;
+      const int j = (w < pad1) ? p.np : 2 * p.ksteps + p.np2;
       sts128(sbase + PAIR_OFF_A + (uint32_t)s * slot_bytes + (uint32_t)(j * PAIR_PLANE + c * 16), 0u, 0u, 0u, 0u);
     }
     if (threadIdx.x < 3 * PAIR_NBLK_MAX) {                            // bias | scale | shift of this pair's columns (zeros / ones where absent)
@@ -182,6 +202,15 @@ conv_pair_kernel(const PairParams p) {
               }
             }
           }
+          if (MODE == ITG_CONV3X3 && p.ksteps2 > 0) {                   // folded 1x1 shortcut: centre tap of the second input's planes, weights of tap 9
+            const uint32_t ak2 = ak + (uint32_t)(2 * p.ksteps) * (PAIR_PLANE / 16) + (uint32_t)(HALO_W + 1);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              if (ks < p.ksteps2)
+                umma2_f16(d, desc_noswz(ak2 + (uint32_t)(2 * ks) * (PAIR_PLANE / 16), PAIR_PLANE / 16, HALO_W),
+                          desc_noswz(w16 + (uint32_t)(2 * ks) * nh16 + 9u * tap16, nh16, 8), p.idesc, 1u);
+            }
+          }
           umma2_commit(bar_a_empty + 8 * s);
           umma2_commit(bar_acc_full + 8 * b);
         }
@@ -201,16 +230,31 @@ conv_pair_kernel(const PairParams p) {
     // (a 1x1 conv reads no neighbours: only the 16 x 8 interior of the halo tile is fetched; the ring around it is never addressed)
     constexpr int ROWS = MODE == ITG_CONV3X3 ? HALO_H : TILE_H, COLS = MODE == ITG_CONV3X3 ? HALO_W : TILE_W, OFF = MODE == ITG_CONV3X3 ? 0 : 1;
     const int row_chunks = COLS * p.np, tile_chunks = ROWS * row_chunks;
-    uint32_t goff[PAIR_LD_ITERS], soff[PAIR_LD_ITERS];                   // element offset from the halo origin | shared offset, hy << 16, hx << 24 (hy = 31: none)
+    const int row_chunks2 = TILE_W * p.np2, tile_chunks2 = (MODE == ITG_CONV3X3 && p.in2 != nullptr) ? TILE_H * row_chunks2 : 0;
+    // element offset from the halo origin | shared offset in 16-byte units, hy << 16, hx << 24, second input << 31 (hy = 31: none)
+    uint32_t goff[PAIR_LD_ITERS], soff[PAIR_LD_ITERS];
 #pragma unroll
     for (int i = 0; i < PAIR_LD_ITERS; ++i) {
       const int q = lt + i * PAIR_LOADERS * 32;
-      const int ry = q / row_chunks, r = q - ry * row_chunks;
-      const int rx = r / p.np, c = r - rx * p.np;
-      const int hy = ry + OFF, hx = rx + OFF;
-      goff[i] = (uint32_t)((hy * p.in_pitch + hx) * p.in_c + c * 8);
-      soff[i] = q < tile_chunks ? ((uint32_t)(c * PAIR_PLANE + (hy * HALO_W + hx) * 16) | ((uint32_t)hy << 16) | ((uint32_t)hx << 24)) : (31u << 16);
+      if (q < tile_chunks) {
+        const int ry = q / row_chunks, r = q - ry * row_chunks;
+        const int rx = r / p.np, c = r - rx * p.np;
+        const int hy = ry + OFF, hx = rx + OFF;
+        goff[i] = (uint32_t)((hy * p.in_pitch + hx) * p.in_c + c * 8);
+        soff[i] = (uint32_t)(c * (PAIR_PLANE / 16) + hy * HALO_W + hx) | ((uint32_t)hy << 16) | ((uint32_t)hx << 24);
+      } else if (q < tile_chunks + tile_chunks2) {                      // the second input: interior of the tile only (a 1x1 conv)
+        const int q2 = q - tile_chunks;
+        const int ry = q2 / row_chunks2, r = q2 - ry * row_chunks2;
+        const int rx = r / p.np2, c = r - rx * p.np2;
+        const int hy = ry + 1, hx = rx + 1;
+        goff[i] = (uint32_t)((hy * p.in_pitch + hx) * p.in2_c + c * 8);
+        soff[i] = (uint32_t)((2 * p.ksteps + c) * (PAIR_PLANE / 16) + hy * HALO_W + hx) | ((uint32_t)hy << 16) | ((uint32_t)hx << 24) | (1u << 31);
+      } else {
+        goff[i] = 0;
+        soff[i] = 31u << 16;
+      }
     }
+    const T* in2 = reinterpret_cast<const T*>(p.in2) + (size_t)p.in2_cg_off * 8;
     uint32_t s = 0, sph = 0;                                            // slot being filled, its phase
     uint32_t ps = 0;                                                    // oldest unpublished slot
     int unpub = 0;                                                      // committed, unpublished tiles
@@ -247,13 +291,15 @@ conv_pair_kernel(const PairParams p) {
       ITG_SACC(0, tl);
       const uint32_t dst = a_smem + s * slot_bytes;
       const T* src0 = in + ((size_t)y0 * p.in_pitch + x0) * (size_t)p.in_c;
+      const T* src2 = in2 + ((size_t)y0 * p.in_pitch + x0) * (size_t)p.in2_c;
       if (!(p.exp & 1)) {
 #pragma unroll
         for (int i = 0; i < PAIR_LD_ITERS; ++i) {
-          const int hy = (int)((soff[i] >> 16) & 31u), hx = (int)(soff[i] >> 24);
+          const int hy = (int)((soff[i] >> 16) & 31u), hx = (int)((soff[i] >> 24) & 31u);
           if (hy != 31) {
             const bool valid = hy < hy_lim && hx < hx_lim;
-            cp_async16_zfill(dst + (soff[i] & 0xffffu), valid ? src0 + goff[i] : in, valid);
+            const T* src = (soff[i] >> 31) ? src2 : src0;
+            cp_async16_zfill(dst + ((soff[i] & 0xffffu) << 4), valid ? src + goff[i] : in, valid);
           }
         }
       }

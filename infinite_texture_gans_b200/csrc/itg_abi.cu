@@ -521,7 +521,16 @@ bool pair_eligible(const itg_conv_desc& d) {
   if (d.k_pad > 128) return false;
   if (d.out_img || d.out_f32 || d.mod_x || d.res_kind == ITG_RES_F32) return false;      // final conv / SSM embed / fp32 residual: other kernels
   const int nblocks = (d.n_pad + itg::PAIR_NBLK_MAX - 1) / itg::PAIR_NBLK_MAX;
-  return nblocks <= 4 && sm_count() >= 2 * nblocks;
+  if (nblocks > 4 || sm_count() < 2 * nblocks) return false;
+  if (d.in2) {                                      // folded 1x1 shortcut: both inputs of a tile must fit a ring slot twice over
+    if (d.mode != ITG_CONV3X3 || d.in_pitch != 0 || !d.w2 || d.k2 <= 0 || d.k2 % 8 || d.k2 > d.k2_pad || d.k2_pad > 128 || d.k2_pad % 16 ||
+        d.in2_c % 8 || d.in2_c_off % 8 || d.in2_c_off + d.k2 > d.in2_c)
+      return false;
+    const int planes = 2 * ((d.k / 8 + 1) / 2) + 2 * ((d.k2 / 8 + 1) / 2);
+    const int chunks = itg::HALO_PX * (d.k / 8) + itg::TILE_W * itg::TILE_H * (d.k2 / 8);
+    if (2 * planes > itg::PAIR_A_PLANES || chunks > itg::PAIR_LD_ITERS * itg::PAIR_LOADERS * 32) return false;
+  }
+  return true;
 }
 // ... and where they are the better choice (AUTO)
 bool pair_preferred(const itg_conv_desc& d) {
@@ -538,7 +547,7 @@ bool pair_preferred(const itg_conv_desc& d) {
 
 template <typename T>
 int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
-  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 or 1x1 conv with 16-bit operands, k_pad <= 128, n_pad <= 256 and grid outputs");
+  if (!pair_eligible(d)) return fail(ITG_ERR_UNSUPPORTED, "conv: the CTA-pair kernel needs a 3x3 or 1x1 conv with 16-bit operands, k_pad <= 128, n_pad <= 256 and grid outputs (second input: 3x3 only, both inputs of a tile within half the activation ring)");
   itg::PairParams p;
   memset(&p, 0, sizeof(p));
   p.m_h = d.in_h; p.m_w = d.in_w;
@@ -549,7 +558,12 @@ int launch_pair(const itg_conv_desc& d, cudaStream_t st) {
   p.in_cg_off = d.in_c_off / 8;
   p.np = d.k / 8;                                   // validate(): k % 8 == 0, k <= k_pad
   p.ksteps = (p.np + 1) / 2;
-  p.slot_planes = 2 * p.ksteps;
+  if (d.in2) {
+    p.in2 = d.in2; p.in2_c = d.in2_c; p.in2_cg_off = d.in2_c_off / 8;
+    p.np2 = d.k2 / 8; p.ksteps2 = (p.np2 + 1) / 2;
+    p.w2 = d.w2; p.k2_pad = d.k2_pad;
+  }
+  p.slot_planes = 2 * (p.ksteps + p.ksteps2);
   p.nring = itg::PAIR_A_PLANES / p.slot_planes;
   if (p.nring > itg::PAIR_MAX_SLOTS) p.nring = itg::PAIR_MAX_SLOTS;
   p.w = d.w; p.n_pad = d.n_pad; p.k_pad = d.k_pad;
@@ -728,6 +742,10 @@ int itg_conv_fwd(const itg_conv_desc* desc, void* stream) {
   if (rc != ITG_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int impl = d.impl;
+  if (d.in2) {                                      // the folded shortcut exists in the CTA-pair kernel only
+    if (impl == ITG_IMPL_AUTO) impl = ITG_IMPL_PAIR;
+    if (impl != ITG_IMPL_PAIR) return fail(ITG_ERR_UNSUPPORTED, "conv: a second input (in2) is served by the CTA-pair kernel only");
+  }
   if (impl == ITG_IMPL_AUTO)
     impl = (d.dtype == ITG_F32) ? ITG_IMPL_SPLIT : (pair_preferred(d) ? ITG_IMPL_PAIR : (tile_eligible(d) ? ITG_IMPL_TILE : ITG_IMPL_UMMA));
   if (impl == ITG_IMPL_SPLIT) {

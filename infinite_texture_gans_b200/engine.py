@@ -28,7 +28,7 @@ import torch
 from . import _lib as L
 from . import packing as PK
 from .config import GenConfig
-from .ops import AttentionOp, ConvOp, Grid, SsmOp, c_store
+from .ops import AttentionOp, ConvOp, Grid, SsmOp, c_store, pair_fold_eligible
 
 PRECISIONS = {
     # name: (torch dtype, conv implementation)
@@ -98,6 +98,8 @@ class PackedWeights:
             conv3(p + "conv2.conv.")
             if ci != co:
                 conv1(p + "conv3.")
+            if ssm_mode and ci != co:              # bias of conv2 with the 1x1 shortcut folded in (one accumulator, itg_conv_desc.in2)
+                put(p + "conv2f.b", t[p + "conv2.conv.b"] + t[p + "conv3.b"])
             if ssm_mode:
                 ssm(p + "bn1.", ci)
                 ssm(p + "bn2.", co)
@@ -168,6 +170,9 @@ class Plan:
         if fuse_ssm is None:
             fuse_ssm = impl == L.IMPL_AUTO and self.dtype != torch.float32 and not os.environ.get("ITG_SSM_UNFUSED")
         self.fuse_ssm = bool(fuse_ssm) and cfg.type_norm == "SSM"
+        # ... and the 1x1 shortcut of an SSM block (conv3 on the bn3 output, at the block's output resolution) folded into its conv2 as a second
+        # input of the CTA-pair kernel where both tiles fit (blocks 4 and 5 of the 34 Generator): one launch and one tensor less per block
+        self.fold_shortcut = self.fuse_ssm and not os.environ.get("ITG_NO_FOLD")
         self.pre_tanh = pre_tanh      # parity aid: the final conv also leaves its fp32 pre-activation (generators.py:119) in self.out_pre
         self.img_layout = img_layout
         self.border = L.BORDER_REPLICATE if cfg.border_is_replicate else L.BORDER_CONSTANT
@@ -214,13 +219,13 @@ class Plan:
 
     def _conv(self, name, mode, src: _VGrid, wkey: str, *, k=None, out_raw=None, out_act=None, norm=None,
               leak=None, linear=False, border=None, res=None, res_shift=0, mod=None,
-              mod_shift=0, mod_prefix=None, window=None, out_hw=None, out_c=None, img=False):
-        self._touch(src, out_raw, out_act, res, mod)
+              mod_shift=0, mod_prefix=None, window=None, out_hw=None, out_c=None, img=False, in2=None, w2key=None, bkey=None):
+        self._touch(src, out_raw, out_act, res, mod, in2)
         self._note_consumer(src)
         self._steps.append(("conv", dict(name=name, mode=mode, src=src, wkey=wkey, k=k, out_raw=out_raw, out_act=out_act,
                                          norm=norm, leak=leak, linear=linear, border=border, res=res,
                                          res_shift=res_shift, mod=mod, mod_shift=mod_shift, mod_prefix=mod_prefix,
-                                         window=window, out_hw=out_hw, out_c=out_c, img=img)))
+                                         window=window, out_hw=out_hw, out_c=out_c, img=img, in2=in2, w2key=w2key, bkey=bkey)))
 
     def _halo(self, name: str, g: _VGrid, r: int):
         self._halo_tmp.append([len(self._steps) - 1, name, g, r, -1])
@@ -350,23 +355,28 @@ class Plan:
             a2 = self._g(f"a.{p}conv2", H, W, c_store(co))
             self._ssm_norm(p + "bn2.", taps, t, 0, a2, False, self.border, k - 1)
             self._halo(p + "conv2", a2, r)
+            fold = {}
             if ci != co:
                 s_in = self._g(f"sin.{p}", H, W, c_store(ci))
                 self._ssm_norm(p + "bn3.", taps, h_raw, x_shift, s_in, True, L.BORDER_NONE, k - 1)
-                s = self._g(f"s.{p}", H, W, c_store(co))
-                self._conv(p + "conv3", L.CONV1X1, s_in, p + "conv3.", out_raw=s)
-                res, res_shift = s, 0
+                if self.fold_shortcut and pair_fold_eligible(c_store(co), c_store(ci), co):
+                    fold = dict(in2=s_in, w2key=p + "conv3.", bkey=p + "conv2f.b")     # conv2 = conv3x3(a2) + conv1x1(s_in), one launch
+                    res, res_shift = None, 0
+                else:
+                    s = self._g(f"s.{p}", H, W, c_store(co))
+                    self._conv(p + "conv3", L.CONV1X1, s_in, p + "conv3.", out_raw=s)
+                    res, res_shift = s, 0
             else:
                 res, res_shift = h_raw, x_shift
             att_here = k == 3 and cfg.attention
             if last and not att_here:
                 a_last = self._g("a.final", H, W, c_store(co))
                 self._conv(p + "conv2", L.CONV3X3, a2, p + "conv2.conv.", out_act=a_last, border=self.border, res=res,
-                           res_shift=res_shift)
+                           res_shift=res_shift, **fold)
                 h_raw = None
             else:
                 h_new = self._g(f"h{k}", H, W, c_store(co))
-                self._conv(p + "conv2", L.CONV3X3, a2, p + "conv2.conv.", out_raw=h_new, res=res, res_shift=res_shift)
+                self._conv(p + "conv2", L.CONV3X3, a2, p + "conv2.conv.", out_raw=h_new, res=res, res_shift=res_shift, **fold)
                 if att_here:
                     h_att = self._g(f"h{k}.att", H, W, c_store(co))
                     self._attention(h_new, h_att, None, None)
@@ -453,8 +463,10 @@ class Plan:
         cfg, w = self.cfg, self.w
         src: Grid = a["src"].grid
         wt = w[a["wkey"] + "w"]
-        op = ConvOp(mode=a["mode"], src=src, w=wt, k=a["k"] if a["k"] is not None else src.c, bias=w[a["wkey"] + "b"],
-                    impl=self.impl, name=a["name"])
+        op = ConvOp(mode=a["mode"], src=src, w=wt, k=a["k"] if a["k"] is not None else src.c,
+                    bias=w[a["bkey"]] if a.get("bkey") else w[a["wkey"] + "b"], impl=self.impl, name=a["name"])
+        if a.get("in2") is not None:                # folded 1x1 shortcut (CTA-pair kernel)
+            op.in2, op.w2, op.k2, op.impl = a["in2"].grid, w[a["w2key"] + "w"], a["in2"].grid.c, L.IMPL_PAIR
         if a["window"] is not None:                 # valid conv on the over-sized SSM hidden map
             H, W = a["window"]
             op.in_h, op.in_w, op.in_pitch = H, W, src.w + 2

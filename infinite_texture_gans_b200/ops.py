@@ -33,6 +33,17 @@ def n_pad_of(n: int) -> int:
     return round_up(n16, 16 * nb)
 
 
+def pair_fold_eligible(k: int, k2: int, n: int) -> bool:
+    """Can a 3x3 conv with k stored input channels take a folded 1x1 shortcut over k2 stored channels (itg_conv_desc.in2)?  Mirror of
+    pair_eligible() in csrc/itg_abi.cu: both inputs of a 16x8 tile within half the activation ring (45 planes) and within the loaders'
+    16 x 192 sixteen-byte chunks; <= 128 channels each; <= 256 GEMM columns."""
+    if k > 128 or k2 > 128 or n_pad_of(n) > 256:
+        return False
+    planes = 2 * ((k // 8 + 1) // 2) + 2 * ((k2 // 8 + 1) // 2)
+    chunks = 180 * (k // 8) + 128 * (k2 // 8)
+    return 2 * planes <= 45 and chunks <= 16 * 192
+
+
 def k_pad_of(k: int) -> int:
     """Padded contraction length per tap: one 32/64-byte swizzle row, or whole 128-byte rows."""
     return 16 if k <= 16 else (32 if k <= 32 else round_up(k, 64))
@@ -102,6 +113,10 @@ class ConvOp:
     patch: int = 0
     impl: int = L.IMPL_AUTO
     name: str = ""
+    # optional second input: the block's 1x1 shortcut folded into this 3x3 conv (itg_conv_desc.in2; CTA-pair kernel only)
+    in2: Optional[Grid] = None
+    w2: Optional[torch.Tensor] = None   # [1, n_pad, k2_pad]
+    k2: int = 0
 
     @property
     def m_h(self) -> int:
@@ -190,6 +205,13 @@ class CudaBackend:
         d.scale, d.shift, d.leak, d.act_linear = L.ptr(op.scale), L.ptr(op.shift), float(op.leak), int(op.act_linear)
         d.out_f32, d.out_img = L.ptr(op.out_f32), L.ptr(op.out_img)
         d.img_c, d.img_layout, d.patch = op.img_c, op.img_layout, op.patch
+        if op.in2 is not None:
+            if op.w2 is None or op.w2.dtype != src.buf.dtype or not op.w2.is_contiguous() or op.w2.shape[1] != op.w.shape[1]:
+                raise L.ItgError(f"conv {op.name}: w2 must be a contiguous [1, n_pad, k2_pad] tensor of the activations' dtype")
+            if (op.in2.h, op.in2.w) != (op.m_h, op.m_w) or op.in2.buf.dtype != src.buf.dtype:
+                raise L.ItgError(f"conv {op.name}: the second input must have the first one's interior size and dtype")
+            d.in2, d.in2_c, d.in2_c_off, d.k2 = L.ptr(op.in2.buf), op.in2.c, 0, op.k2 or op.in2.c
+            d.w2, d.k2_pad = L.ptr(op.w2), op.w2.shape[2]
         return d
 
     def compile_conv(self, op: ConvOp):

@@ -86,6 +86,9 @@ class EmulatorBackend:
 
         if op.mode == L.CONV3X3:
             acc = sum(tap(t // 3 - 1, t % 3 - 1, t) for t in range(9))
+            if op.in2 is not None:                             # folded 1x1 shortcut: same accumulator
+                k2 = op.k2 or op.in2.c
+                acc = acc + op.in2.interior[..., :k2].float() @ op.w2.float()[0, :, :k2].t()
         elif op.mode == L.CONV1X1:
             acc = tap(0, 0, 0)
         else:

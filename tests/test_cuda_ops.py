@@ -183,6 +183,32 @@ def test_conv_matches_emulator(be, case, precision, impl):
     _check_conv(opc, opg, dtype)
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("H,W,c2,c3,cout,ex", [
+    (50, 38, 26, 52, 26, dict(raw=True, border=L.BORDER_NONE)),                       # block 5 of the 34 Generator: conv2 26 -> 26 + shortcut 52 -> 26
+    (33, 70, 52, 104, 52, dict(raw=True, border=L.BORDER_NONE)),                      # block 4: two ring slots
+    (136, 120, 26, 52, 26, dict(act=True, border=L.BORDER_REPLICATE)),                # last block: activated, framed output
+    (9, 7, 16, 32, 16, dict(raw=True, act=True, res=0, border=L.BORDER_CONSTANT)),    # with a residual on top
+])
+def test_conv_with_folded_shortcut_matches_emulator(be, precision, H, W, c2, c3, cout, ex):
+    """itg_conv_desc.in2: conv3x3(in) + conv1x1(in2) in one accumulator (the block's 1x1 shortcut folded into conv2, CTA-pair kernel)."""
+    dtype = DT[precision]
+    opc = _make_conv("3x3", H, W, c2, cout, ex, dtype, L.IMPL_AUTO, seed=H * 100 + W + c3)
+    g = torch.Generator().manual_seed(c3 * 31 + H)
+    k3 = c_store(c3)
+    in2 = _grid(H, W, k3, dtype, g)
+    in2.buf[..., c3:] = 0
+    opc.in2, opc.k2 = in2, k3
+    opc.w2 = PK.pack_conv1x1(torch.randn(cout, c3, 1, 1, generator=g) / math.sqrt(c3), dtype)
+
+    def to_dev(op):
+        d = _conv_to_dev(op)
+        d.in2, d.w2 = Grid(op.in2.buf.clone().cuda(), H, W, k3), op.w2.clone().cuda()
+        return d
+    opg = _run_both(be, opc, to_dev)
+    _check_conv(opc, opg, dtype)
+
+
 @pytest.mark.parametrize("precision,impl", [("fp32", L.IMPL_DIRECT), ("fp32", L.IMPL_SPLIT), ("fp16", L.IMPL_UMMA), ("fp16", L.IMPL_TILE),
                                             ("fp16", L.IMPL_PAIR)], ids=["direct", "split", "umma", "tile", "pair"])
 @pytest.mark.parametrize("mode,H,W,cin,cout", [("3x3", 33, 47, 52, 26), ("1x1", 17, 9, 64, 64), ("3x3", 130, 21, 26, 13)])

@@ -65,7 +65,9 @@ def test_fused_ssm_plan_matches_reference():
     n_norms = sum(3 if ci != co else 2 for ci, co in eng.cfg.block_channels())
     assert fused.fuse_ssm and kinds.count("ssm") == n_norms and "pack_map" not in kinds
     assert [k for k, _ in split.ops].count("pack_map") == eng.cfg.n_layers_G
-    assert fused.n_launches == split.n_launches - n_norms - eng.cfg.n_layers_G
+    n_fold = sum(1 for k, o in fused.ops if k == "conv" and o.in2 is not None)        # 1x1 shortcuts folded into their conv2 (second input)
+    assert n_fold == sum(1 for ci, co in eng.cfg.block_channels() if ci != co) and all(o.in2 is None for k, o in split.ops if k == "conv")
+    assert fused.n_launches == split.n_launches - n_norms - eng.cfg.n_layers_G - n_fold
     assert fused.arena_bytes < 0.5 * split.arena_bytes
     outs = []
     for p in (fused, split):
@@ -143,7 +145,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), s
     lib2 = L.load()
-    assert lib2.itg_version() == 2
+    assert lib2.itg_version() == 3
     assert lib2.itg_conv_desc_size() == ctypes.sizeof(L.ConvDesc)
     assert lib2.itg_ssm_desc_size() == ctypes.sizeof(L.SsmDesc)
 
