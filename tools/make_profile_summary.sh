@@ -48,7 +48,7 @@ echo '```'
 python tools/show_profile.py gpurun_out/${R}_lp_cfg3.json
 echo '```'
 echo
-echo "## ncu --set full (launches of blocks 4-5 of one pass: block4.conv2, block5.bn1.ssm, block5.conv1, block5.bn2.ssm, block5.bn3.ssm, block5.conv3, block5.conv2, final)"
+echo "## ncu --set full (16 consecutive SSM / pair / thin-layer launches of the second pass: blocks 4-5 and the final conv)"
 echo
 python tools/ncu_summary.py raw gpurun_out/${R}_prof_cfg3_raw.csv
 } > profiles/${R}_summary.md
