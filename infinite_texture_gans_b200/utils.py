@@ -230,6 +230,70 @@ def sample_from_gen_PatchByPatch_test(netG, z_dim=128, base_res=4, map_dim=1, nu
     return img if return_on_device else img.cpu()
 
 
+VIRTUAL_ROWS = 1 << 24      # patch rows of the counter-based noise field a seeded stream draws from (2^31 pixels of height at P = 128)
+
+
+def stream_texture_rows(netG, output_resolution_width: int, *, seed: Optional[int] = None, noise_rows=None, steps: Optional[int] = None,
+                        num_patches_height: int = 3, num_patches_width: int = 3):
+    """Top-to-bottom generator of a texture of UNBOUNDED height: the shipped sub-image schedule (utils.py:317-392) run one
+    sub-image ROW per iteration, yielding the finished patch rows of each as a device tensor (1, img_ch, rows * P, W) -- (nph - 1) patch rows per
+    iteration, nph for the last one.  Device memory is O(one sub-image row) whatever the height: the noise of nph patch rows, one band canvas
+    and LocalPadder's halo state (the row above + the sub-image to the left, layers.py:103-143); nothing of the texture is kept.
+
+    steps: number of sub-image rows; the last one is generated with the 'last_row' locations (bottom outer padding).  None = endless
+           (every row after the first is an 'inter_row'; stop iterating when enough has been produced).
+    Noise: `seed` draws patch rows on demand from the device-side counter-based field (draw_noise_device on a virtual grid of
+           VIRTUAL_ROWS patch rows: any two streams with the same seed and width agree row for row), or `noise_rows(ih)` returns
+           (z, maps) of patch rows [ih * (nph - 1), ih * (nph - 1) + nph) in draw_noise's 4-D layout (host or device).
+    With `noise_rows` slicing a full grid and `steps` = its steps_h, the concatenated output equals
+    sample_from_gen_PatchByPatch_test(..., schedule='sequential') bit for bit (same launches in the same order)."""
+    G = _unwrap(netG)
+    cfg = G.cfg
+    b, nph, npw = cfg.base_res, num_patches_height, num_patches_width
+    geo = patch_grid_geometry(2 * cfg.patch_px, output_resolution_width, cfg.n_layers_G, b, nph, npw)
+    P, tw, sw = geo["P"], geo["total_w"], geo["steps_w"]
+    if (seed is None) == (noise_rows is None):
+        raise ValueError("pass either seed= (device-side counter-based noise) or noise_rows= (a callable returning each row's noise)")
+    if steps is not None and steps < 1:
+        raise ValueError("steps must be >= 1")
+    dev = next(G.parameters()).device
+
+    def rows_of(ih):
+        if noise_rows is not None:
+            z, maps = noise_rows(ih)
+            return z[:1].to(dev), None if maps is None else [m[:1].to(dev) for m in maps]
+        py = ih * (nph - 1)
+        if py + nph > VIRTUAL_ROWS:
+            raise RuntimeError("the seeded noise field is exhausted (2^24 patch rows)")
+        z, maps = draw_noise_device(cfg, VIRTUAL_ROWS, tw, seed, rows=(py, py + nph), device=dev)
+        return z.unsqueeze(0), None if maps is None else [m[None, None] for m in maps]
+
+    saved = (LocalPadder.num_patches_h, LocalPadder.num_patches_w)
+    LocalPadder.num_patches_h, LocalPadder.num_patches_w = nph, npw
+    try:
+        ih = 0
+        while steps is None or ih < steps:
+            last = steps is not None and ih == steps - 1
+            z_rows, maps_rows = rows_of(ih)
+            keep = nph if last else nph - 1
+            band = torch.empty((1, G.img_ch, keep * P, tw * P), dtype=torch.float32, device=dev)
+            row = "1st_row_last_row" if (last and ih == 0) else ("1st_row" if ih == 0 else ("last_row" if last else "inter_row"))
+            for iw in range(sw):
+                col = "_1st_col_last_col" if sw == 1 else ("_1st_col" if iw == 0 else ("_last_col" if iw == sw - 1 else "_inter_col"))
+                px = iw * (npw - 1)
+                z_sub = z_rows[:, :, :, px * b:(px + npw) * b + 2]
+                maps = None
+                if maps_rows is not None:
+                    maps = [m[:, :, :, px * b * 2 ** i:(px + npw) * b * 2 ** i + 4].contiguous() for i, m in enumerate(maps_rows)]
+                sub = merge_patches_into_image(G(z_sub.contiguous(), maps, row + col), nph, npw)
+                kw = npw * P if iw == sw - 1 else (npw - 1) * P              # utils.py:364-377
+                band[:, :, :, px * P:px * P + kw] = sub[:, :, :keep * P, :kw]
+            yield band[:, :, :, :output_resolution_width]
+            ih += 1
+    finally:
+        LocalPadder.num_patches_h, LocalPadder.num_patches_w = saved
+
+
 def tile_process(img: torch.Tensor, model, scale: int = 4, tile_size: int = 32, tile_pad: int = 8) -> torch.Tensor:
     """utils.tile_process (utils.py:401-470): run `model` on overlapping tiles of the latent `img` (N, C, h, w) and paste the centres
     into the (N, 3, h*scale, w*scale) output.  Same tiling arithmetic; the output stays on the device of the tiles."""

@@ -83,6 +83,33 @@ def test_sequential_schedule_other_subimage_sizes_on_the_device(nps, H, W):
         assert (got - ref).abs().max().item() <= TOL[precision]
 
 
+@pytest.mark.parametrize("norm", ["BN", "SSM"])
+def test_row_stream_with_device_noise_on_the_device(norm):
+    """utils.stream_texture_rows(seed=...): unbounded-height streaming with O(sub-image row) device state, noise drawn row by row from the
+    counter-based field.  The first bands of an endless stream == the sequential sampler fed the same field's rows (bit for bit, fp16),
+    and the stream against Oracle B on that noise."""
+    import infinite_texture_gans_b200 as itg
+    kw = dict(z_dim=16, G_ch=8, n_layers_G=4, attention=True, leak=0.02, type_norm=norm, outer_padding="replicate")
+    ocfg = O.GenCfg(**kw)
+    sd = O.make_state_dict(ocfg, 9, stress=True)
+    net = make_generator(kw, sd, "fp16", "cuda")
+    P, seed, W = net.cfg.patch_px, 77, 5 * 32 - 5
+    geo = itg.utils.patch_grid_geometry(7 * P, W, 4, 4, 3, 3)                    # 3 sub-image rows of a 7-patch-row texture
+    z, maps = itg.utils.draw_noise_device(net.cfg, itg.utils.VIRTUAL_ROWS, geo["total_w"], seed, rows=(0, geo["total_h"]), device="cuda")
+    noise = (z.unsqueeze(0).cpu(), None if maps is None else [m[None, None].cpu() for m in maps])
+    ref = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=16, output_resolution_height=7 * P, output_resolution_width=W,
+                                                      schedule="sequential", noise=noise)
+    stream = itg.utils.stream_texture_rows(net, W, seed=seed)
+    bands = [next(stream).cpu().clone() for _ in range(2)]
+    stream.close()
+    assert torch.equal(torch.cat(bands, 2), ref[:, :, :4 * P])                   # rows before the texture's last sub-image row
+    finite = torch.cat([t.cpu() for t in itg.utils.stream_texture_rows(net, W, seed=seed, steps=3)], 2)
+    assert torch.equal(finite, ref)
+    with torch.no_grad():
+        want = O.sample_patch_by_patch(sd, ocfg, 7 * P, W, noise[0], noise[1])
+    assert (finite - want).abs().max().item() <= TOL["fp16"]
+
+
 def test_forward_signature_and_patch_layout():
     """netG(z, maps, image_location) returns (nph*npw, img_ch, P, P) patches in row-major order (generators.py:86-124)."""
     import infinite_texture_gans_b200 as itg

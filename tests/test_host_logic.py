@@ -210,6 +210,40 @@ def test_sequential_protocol_other_subimage_sizes(nps, H, W):
     assert (got - ref).abs().max().item() <= 5e-5
 
 
+@pytest.mark.parametrize("name,nps", [("gen_bn4_att_rep", 3), ("gen_ssm4_att_rep", 3), ("gen_bn4_att_rep", 4)])
+def test_row_stream_equals_the_sequential_sampler(name, nps):
+    """utils.stream_texture_rows yields the texture band by band with O(sub-image row) state; fed the rows of a full noise grid it is the
+    shipped schedule itself: the concatenated bands equal sample_from_gen_PatchByPatch_test(schedule='sequential') bit for bit, and an
+    endless stream's first bands equal those of a longer texture (no 'last_row' is ever taken)."""
+    d, kw, ocfg, sd, _, _ = load_case(name)
+    net = make_generator(kw, sd, "fp32", backend=EmulatorBackend())
+    P, b = net.cfg.patch_px, net.cfg.base_res
+    H, W = (2 * (nps - 1) + 1) * P - 7, (2 * (nps - 1) + 1) * P - 3           # two sub-image steps each way, not multiples of the patch
+    geo = itg.utils.patch_grid_geometry(H, W, kw["n_layers_G"], b, nps, nps)
+    torch.manual_seed(11)
+    z, maps = itg.utils.draw_noise(1, kw["z_dim"], b, kw["n_layers_G"], 1, kw["type_norm"], geo["total_h"], geo["total_w"])
+    ref = itg.utils.sample_from_gen_PatchByPatch_test(net, z_dim=kw["z_dim"], num_patches_height=nps, num_patches_width=nps,
+                                                      output_resolution_height=H, output_resolution_width=W, schedule="sequential", noise=(z, maps))
+
+    def rows(ih):
+        py = ih * (nps - 1)
+        zr = z[:, :, py * b:(py + nps) * b + 2]
+        mr = None if maps is None else [m[:, :, py * b * 2 ** i:(py + nps) * b * 2 ** i + 4] for i, m in enumerate(maps)]
+        return zr, mr
+
+    bands = list(itg.utils.stream_texture_rows(net, W, noise_rows=rows, steps=geo["steps_h"], num_patches_height=nps, num_patches_width=nps))
+    assert [t.shape[2] for t in bands] == [(nps - 1) * P] * (geo["steps_h"] - 1) + [nps * P]
+    got = torch.cat(bands, 2)[:, :, :H]
+    assert torch.equal(got.cpu(), ref)
+    endless = itg.utils.stream_texture_rows(net, W, noise_rows=rows, num_patches_height=nps, num_patches_width=nps)
+    first = next(endless)
+    endless.close()
+    assert torch.equal(first.cpu(), ref[:, :, :(nps - 1) * P])
+    assert (itg.LocalPadder.num_patches_h, itg.LocalPadder.num_patches_w) != (None, None)
+    with pytest.raises(ValueError, match="either seed"):
+        next(itg.utils.stream_texture_rows(net, W))
+
+
 def test_build_z_build_maps_and_init_weight_match_the_reference():
     """utils.build_z / utils.build_maps (utils.py:221-256) and layers.init_weight (utils.py:745-762) against outputs of the unmodified
     reference under the same torch seeds (tests/golden/aux.npz, written by make_golden.py): same draw order, same overlapping
