@@ -1,6 +1,7 @@
-// 3x3 local-padding convolution (conv2d_lp, models/layers.py:29-36) with K <= 128 input channels per tap on CTA PAIRS
+// 3x3 (and 1x1) local-padding convolution (conv2d_lp, models/layers.py:29-36) with K <= 128 input channels per tap on CTA PAIRS
 // (tcgen05.mma.cta_group::2): the pipeline of the SSM pair kernel (ssm_fused2.cuh) fed from global memory instead of from the
-// mlp_shared GEMM.  It serves the 104 -> 104 / 104 -> 52 / 52 -> 52 / 52 -> 26 / 26 -> 26 layers of the 34 Generator's last blocks.
+// mlp_shared GEMM.  It serves the 104 -> 104 / 104 -> 52 / 52 -> 52 / 52 -> 26 / 26 -> 26 layers and the 1x1 shortcuts of the 34 Generator's
+// last blocks (MODE = ITG_CONV1X1: one tap, only the tile interior is fetched).
 //
 // What it replaces.  The streaming kernel (conv_umma.cuh) fetches a fresh 128-pixel activation tile PER TAP (9 x 32 KB of A plus
 // 9 x 16 KB of weights per tile out of L2: block4.conv1 of cfg3 ran at the L2's bandwidth, 14.6 k cycles per tile for 3.5 k cycles of
@@ -12,7 +13,7 @@
 //     touches 4-5 lines instead of 32; the plane pitch of 2896 B (= 16 mod 128) spreads the chunks of a pixel over the bank groups
 //     (tools/ldgsts_probe.cu: 17-24 cycles per warp instruction against 180 for one pixel per lane).  The lane -> (global offset,
 //     shared offset) table is tile-independent and lives in registers;
-//   * the weights of all taps for the CTA's half of the pair's <= 64 GEMM columns (72 KB) stay in shared memory for the whole launch:
+//   * the weights of all taps for the CTA's half of the pair's <= 64 GEMM columns (80 KB with the shortcut's tenth tap) stay in shared memory for the whole launch:
 //     in steady state the kernel reads each activation once (+ halo) and writes its outputs; wider layers run as column blocks;
 //   * whole tiles are handed over through a ring of 3 (K = 104) / 5 (K = 64) / 8 (K = 32) slots, up to three in flight per loader warp;
 //   * optional second input (itg_conv_desc.in2): the block's 1x1 shortcut folded into its conv2 -- the loaders also fetch the tile interior
@@ -40,7 +41,7 @@ constexpr int PAIR_MAX_SLOTS = 8;
 constexpr int PAIR_HDR = 1024;                                         // barriers | at 256: bias, scale, shift of the pair's 64 columns (fp32)
 constexpr int PAIR_OFF_VEC = 256;
 constexpr int PAIR_OFF_STAGE = PAIR_HDR;                               // 8 epilogue warps x [32 pixels][64 B]: transposition buffer of the coalesced stores
-constexpr int PAIR_OFF_W = PAIR_OFF_STAGE + 8 * 2048;                  // [tap 9][k-group 16, kg used][32 rows, n_half used][16 B]
+constexpr int PAIR_OFF_W = PAIR_OFF_STAGE + 8 * 2048;                  // [tap 10][k-group 16, kg used][32 rows, n_half used][16 B]
 constexpr int PAIR_OFF_A = PAIR_OFF_W + PAIR_W_TAPS * PAIR_KG_MAX * PAIR_NH * 16;
 constexpr int PAIR_LOADERS = 6;                                        // warps 8..13
 constexpr int PAIR_LD_ITERS = 16;                                      // 16-byte chunks per loader thread and tile (launch_pair checks the count)
